@@ -1,0 +1,184 @@
+"""ctypes binding of libhydragen_b200.so (the C ABI declared in include/hydragen_b200.h).
+
+There is NO fallback: if the shared library is missing, or a call fails, an exception is raised.
+torch is used only to hold device memory and to name the current stream.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from typing import Optional, Sequence
+
+import torch
+
+from . import build as _build
+
+HG_F16, HG_BF16, HG_F32 = 0, 1, 2
+HG_MAX_COMBINE = 8
+ABI_VERSION = 1
+
+_DTYPES = {torch.float16: HG_F16, torch.bfloat16: HG_BF16, torch.float32: HG_F32}
+
+# every symbol include/hydragen_b200.h declares: name -> (restype, argtypes)
+_c_void_pp = POINTER(c_void_p)
+SYMBOLS = {
+    "hg_abi_version": (c_int, []),
+    "hg_last_error": (c_char_p, []),
+    "hg_init": (c_int, [c_int]),
+    "hg_sm_count": (c_int, []),
+    "hg_combine_lse": (c_int, [_c_void_pp, _c_void_pp, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "hg_rowwise_attn_fwd": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+         c_int, c_int, c_int, c_int, c_int, c_int,
+         c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+         _c_void_pp, _c_void_pp, c_int, c_float, c_int, c_void_p],
+    ),
+    "hg_prefix_attn_fwd": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
+         c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_void_p],
+    ),
+    "hg_kv_append": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    ),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+_inited_devices: set = set()
+
+
+class HydragenB200Error(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree library and bind every declared symbol.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise HydragenB200Error(
+            f"{path} not found: the CUDA extension has not been built. Run `python -m hydragen_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU or PyTorch fallback for this path."
+        )
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.hg_abi_version() != ABI_VERSION:
+        raise HydragenB200Error(f"ABI mismatch: library {lib.hg_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().hg_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise HydragenB200Error(f"{what} failed ({rc}): {msg}")
+
+
+def ensure_init(device: torch.device):
+    if device.type != "cuda":
+        raise HydragenB200Error(f"hydragen_b200 kernels need CUDA tensors (got device {device}); there is no CPU path")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _inited_devices:
+        _check(load().hg_init(idx), "hg_init")
+        _inited_devices.add(idx)
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPES[dt]
+    except KeyError:
+        raise ValueError(f"unsupported dtype {dt}") from None
+
+
+def _stream(t: torch.Tensor) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> c_void_p:
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def _ptr_table(ts: Sequence[torch.Tensor]):
+    arr = (c_void_p * max(1, len(ts)))()
+    for i, t in enumerate(ts):
+        arr[i] = t.data_ptr()
+    return ctypes.cast(arr, _c_void_pp)
+
+
+# ------------------------------------------------------------------------------------------
+# thin typed wrappers (one per C entry point)
+# ------------------------------------------------------------------------------------------
+
+
+def combine_lse(outs: Sequence[torch.Tensor], lses: Sequence[torch.Tensor], out: torch.Tensor,
+                lse_out: Optional[torch.Tensor]) -> None:
+    ensure_init(out.device)
+    d = out.shape[-1]
+    rows = out.numel() // d if d > 0 else 0
+    with torch.cuda.device(out.device):
+        rc = load().hg_combine_lse(_ptr_table(outs), _ptr_table(lses), len(outs), _ptr(out), _ptr(lse_out), rows, d,
+                                   dtype_code(out.dtype), _stream(out))
+    _check(rc, "hg_combine_lse")
+
+
+def rowwise_attn_fwd(q, k, v, seq_lens, cu_seqlens_k, kv_group_size, causal, out, lse, lk,
+                     kv_strides, partial_outs, partial_lses, sm_scale) -> None:
+    ensure_init(q.device)
+    b, nq, hq, d = q.shape
+    hkv = k.shape[-2]
+    sl_i64 = 0
+    if seq_lens is not None:
+        if seq_lens.dtype == torch.int64:
+            sl_i64 = 1
+        elif seq_lens.dtype != torch.int32:
+            raise ValueError(f"seq_lens must be int32 or int64, got {seq_lens.dtype}")
+    with torch.cuda.device(q.device):
+        rc = load().hg_rowwise_attn_fwd(
+            _ptr(q), _ptr(k), _ptr(v), _ptr(seq_lens), sl_i64, _ptr(cu_seqlens_k), kv_group_size, int(bool(causal)),
+            _ptr(out), _ptr(lse), b, nq, lk, hq, hkv, d,
+            q.stride(0), q.stride(1), q.stride(2), kv_strides[0], kv_strides[1], kv_strides[2],
+            _ptr_table(partial_outs), _ptr_table(partial_lses), len(partial_outs), float(sm_scale),
+            dtype_code(q.dtype), _stream(q))
+    _check(rc, "hg_rowwise_attn_fwd")
+
+
+def prefix_attn_fwd(q, k, v, out, lse, n_groups, q_per_group, n_k_rows, k_len, cu_seqlens_k, max_k_len,
+                    hq, hkv, d, q_stride_row, kv_stride_row, sm_scale) -> None:
+    ensure_init(q.device)
+    with torch.cuda.device(q.device):
+        rc = load().hg_prefix_attn_fwd(
+            _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), n_groups, q_per_group, n_k_rows, k_len,
+            _ptr(cu_seqlens_k), max_k_len, hq, hkv, d, q_stride_row, kv_stride_row, float(sm_scale),
+            dtype_code(q.dtype), _stream(q))
+    _check(rc, "hg_prefix_attn_fwd")
+
+
+def kv_append(k_new, v_new, positions, k_cache, v_cache) -> None:
+    ensure_init(k_new.device)
+    b, nq, hkv, d = k_new.shape
+    lk = k_cache.shape[1]
+    if positions.dtype == torch.int64:
+        pi64 = 1
+    elif positions.dtype == torch.int32:
+        pi64 = 0
+    else:
+        raise ValueError(f"positions must be int32 or int64, got {positions.dtype}")
+    with torch.cuda.device(k_new.device):
+        rc = load().hg_kv_append(_ptr(k_new), _ptr(v_new), _ptr(positions), pi64, _ptr(k_cache), _ptr(v_cache),
+                                 b, nq, lk, hkv, d, dtype_code(k_new.dtype), _stream(k_new))
+    _check(rc, "hg_kv_append")

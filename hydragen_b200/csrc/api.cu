@@ -1,0 +1,177 @@
+// C ABI of hydragen_b200 (see include/hydragen_b200.h): argument validation, error plumbing and
+// device bring-up.  No torch types, no allocation, no synchronisation on any launch path.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace hg {
+
+static thread_local char g_err[512] = "";
+static DeviceInfo g_info;
+static std::mutex g_init_mutex;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // clear the (non-sticky) launch error
+    return set_error(HG_ERR_CUDA, "%s: launch failed: %s", what, cudaGetErrorString(e));
+  }
+  return HG_OK;
+}
+
+const DeviceInfo& device_info() { return g_info; }
+
+static bool valid_dtype(int dtype) { return dtype == HG_F16 || dtype == HG_BF16 || dtype == HG_F32; }
+
+static int fill_partials(PartialTable& t, const void* const* outs, const float* const* lses, int n, const char* who) {
+  if (n < 0 || n > HG_MAX_COMBINE) return set_error(HG_ERR_INVALID_ARGUMENT, "%s: n = %d outside [0, %d]", who, n, HG_MAX_COMBINE);
+  memset(&t, 0, sizeof(t));
+  t.n = n;
+  if (n > 0 && (outs == nullptr || lses == nullptr)) return set_error(HG_ERR_INVALID_ARGUMENT, "%s: null pointer table", who);
+  for (int i = 0; i < n; ++i) {
+    if (outs[i] == nullptr || lses[i] == nullptr) return set_error(HG_ERR_INVALID_ARGUMENT, "%s: null partial %d", who, i);
+    t.outs[i] = outs[i];
+    t.lses[i] = lses[i];
+  }
+  return HG_OK;
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" {
+
+int hg_abi_version(void) { return HG_ABI_VERSION; }
+
+const char* hg_last_error(void) { return g_err; }
+
+int hg_sm_count(void) { return g_info.sm_count; }
+
+int hg_init(int device) {
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  if (g_info.ready && g_info.device == device) return HG_OK;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return set_error(HG_ERR_CUDA, "hg_init: cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return set_error(HG_ERR_UNSUPPORTED, "hg_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                     prop.major, prop.minor);
+  g_info.device = device;
+  g_info.sm_count = prop.multiProcessorCount;
+  g_info.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr)
+    return set_error(HG_ERR_CUDA, "hg_init: cuTensorMapEncodeTiled not found: %s", cudaGetErrorString(e));
+  g_info.encode_tiled = fn;
+  g_info.ready = true;
+  return HG_OK;
+}
+
+int hg_combine_lse(const void* const* outs_host, const float* const* lses_host, int n, void* out, float* lse_out, int64_t rows,
+                   int d, int dtype, void* stream) {
+  if (n < 1) return set_error(HG_ERR_INVALID_ARGUMENT, "combine: n = %d, need at least one input", n);
+  if (!valid_dtype(dtype)) return set_error(HG_ERR_INVALID_ARGUMENT, "combine: unknown dtype %d", dtype);
+  if (rows < 0 || d < 1) return set_error(HG_ERR_INVALID_ARGUMENT, "combine: rows = %lld, d = %d", (long long)rows, d);
+  if (out == nullptr && rows > 0) return set_error(HG_ERR_INVALID_ARGUMENT, "combine: out is null");
+  PartialTable t;
+  int rc = fill_partials(t, outs_host, lses_host, n, "combine");
+  if (rc != HG_OK) return rc;
+  return launch_combine(t, out, lse_out, rows, d, dtype, (cudaStream_t)stream);
+}
+
+int hg_rowwise_attn_fwd(const void* q, const void* k, const void* v, const void* seq_lens, int seq_lens_i64,
+                        const int32_t* cu_seqlens_k, int kv_group_size, int causal, void* out, float* lse, int b, int nq, int lk,
+                        int hq, int hkv, int d, int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h, int64_t kv_stride_b,
+                        int64_t kv_stride_s, int64_t kv_stride_h, const void* const* partial_outs_host,
+                        const float* const* partial_lses_host, int n_partials, float sm_scale, int dtype, void* stream) {
+  if (!valid_dtype(dtype)) return set_error(HG_ERR_INVALID_ARGUMENT, "rowwise: unknown dtype %d", dtype);
+  if (b < 0 || nq < 0 || lk < 0 || hq < 1 || hkv < 1 || d < 1)
+    return set_error(HG_ERR_INVALID_ARGUMENT, "rowwise: bad sizes b=%d nq=%d lk=%d hq=%d hkv=%d d=%d", b, nq, lk, hq, hkv, d);
+  if (hq % hkv != 0) return set_error(HG_ERR_INVALID_ARGUMENT, "rowwise: hq (%d) must be a multiple of hkv (%d)", hq, hkv);
+  if (kv_group_size < 1 || (b % kv_group_size) != 0)
+    return set_error(HG_ERR_INVALID_ARGUMENT, "rowwise: kv_group_size %d must divide b = %d", kv_group_size, b);
+  if (seq_lens != nullptr && kv_group_size != 1)
+    return set_error(HG_ERR_INVALID_ARGUMENT, "rowwise: seq_lens requires kv_group_size == 1");
+  if (b > 0 && nq > 0 && (q == nullptr || out == nullptr)) return set_error(HG_ERR_INVALID_ARGUMENT, "rowwise: null q/out");
+  if (b > 0 && lk > 0 && (k == nullptr || v == nullptr)) return set_error(HG_ERR_INVALID_ARGUMENT, "rowwise: null k/v");
+  const int esz = dtype == HG_F32 ? 4 : 2;
+  const int vec = 16 / esz;
+  if (q_stride_b % vec || q_stride_s % vec || q_stride_h % vec || kv_stride_b % vec || kv_stride_s % vec || kv_stride_h % vec ||
+      reinterpret_cast<uintptr_t>(q) % 16 || reinterpret_cast<uintptr_t>(k) % 16 || reinterpret_cast<uintptr_t>(v) % 16 ||
+      reinterpret_cast<uintptr_t>(out) % 16)
+    return set_error(HG_ERR_UNSUPPORTED, "rowwise: bases and strides must be 16-byte aligned");
+  RowwiseParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_partials(p.partials, partial_outs_host, partial_lses_host, n_partials, "rowwise");
+  if (rc != HG_OK) return rc;
+  for (int i = 0; i < n_partials; ++i)
+    if (reinterpret_cast<uintptr_t>(partial_outs_host[i]) % 16)
+      return set_error(HG_ERR_UNSUPPORTED, "rowwise: partial outs must be 16-byte aligned");
+  p.q = q; p.k = k; p.v = v;
+  p.seq_lens = seq_lens; p.seq_lens_i64 = seq_lens_i64;
+  p.cu_seqlens_k = cu_seqlens_k;
+  p.kv_group_size = kv_group_size;
+  p.causal = causal;
+  p.out = out; p.lse = lse;
+  p.b = b; p.nq = nq; p.lk = lk; p.hq = hq; p.hkv = hkv; p.d = d;
+  p.q_stride_b = q_stride_b; p.q_stride_s = q_stride_s; p.q_stride_h = q_stride_h;
+  p.kv_stride_b = kv_stride_b; p.kv_stride_s = kv_stride_s; p.kv_stride_h = kv_stride_h;
+  p.scale_log2 = sm_scale * kLog2e;
+  return launch_rowwise(p, dtype, (cudaStream_t)stream);
+}
+
+int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int n_groups, int q_per_group,
+                       int64_t n_k_rows, int k_len, const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
+                       int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype, void* stream) {
+  if (!g_info.ready) return set_error(HG_ERR_NOT_INITIALIZED, "prefix: hg_init() has not been called");
+  if (n_groups < 0 || q_per_group < 0 || n_k_rows < 0 || hq < 1 || hkv < 1)
+    return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: bad sizes n_groups=%d q_per_group=%d n_k_rows=%lld hq=%d hkv=%d", n_groups,
+                     q_per_group, (long long)n_k_rows, hq, hkv);
+  if (hq % hkv != 0) return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: hq (%d) must be a multiple of hkv (%d)", hq, hkv);
+  if (cu_seqlens_k == nullptr && (k_len < 0 || (int64_t)n_groups * k_len > n_k_rows))
+    return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: n_groups * k_len (%d * %d) exceeds n_k_rows (%lld)", n_groups, k_len,
+                     (long long)n_k_rows);
+  if (n_groups > 0 && q_per_group > 0 && (q == nullptr || out == nullptr || k == nullptr || v == nullptr))
+    return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: null tensor pointer");
+  if ((int64_t)n_groups * q_per_group > 0x7fffffffLL || n_k_rows > 0x7fffffffLL)
+    return set_error(HG_ERR_UNSUPPORTED, "prefix: row counts must fit int32");
+  (void)max_k_len;
+  PrefixParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.k = k; p.v = v; p.out = out; p.lse = lse;
+  p.n_groups = n_groups; p.q_per_group = q_per_group;
+  p.n_k_rows = n_k_rows; p.k_len = k_len;
+  p.cu_seqlens_k = cu_seqlens_k; p.max_k_len = max_k_len;
+  p.hq = hq; p.hkv = hkv; p.d = d;
+  p.q_stride_row = q_stride_row; p.kv_stride_row = kv_stride_row;
+  p.scale_log2 = sm_scale * kLog2e;
+  return launch_prefix(p, dtype, (cudaStream_t)stream);
+}
+
+int hg_kv_append(const void* k_new, const void* v_new, const void* positions, int positions_i64, void* k_cache, void* v_cache,
+                 int b, int nq, int lk, int hkv, int d, int dtype, void* stream) {
+  if (!valid_dtype(dtype)) return set_error(HG_ERR_INVALID_ARGUMENT, "kv_append: unknown dtype %d", dtype);
+  if (b < 0 || nq < 0 || lk < 1 || hkv < 1 || d < 1) return set_error(HG_ERR_INVALID_ARGUMENT, "kv_append: bad sizes");
+  if (b > 0 && nq > 0 && (!k_new || !v_new || !positions || !k_cache || !v_cache))
+    return set_error(HG_ERR_INVALID_ARGUMENT, "kv_append: null pointer");
+  if (reinterpret_cast<uintptr_t>(k_new) % 16 || reinterpret_cast<uintptr_t>(v_new) % 16 ||
+      reinterpret_cast<uintptr_t>(k_cache) % 16 || reinterpret_cast<uintptr_t>(v_cache) % 16)
+    return set_error(HG_ERR_UNSUPPORTED, "kv_append: pointers must be 16-byte aligned");
+  return launch_kv_append(k_new, v_new, positions, positions_i64, k_cache, v_cache, b, nq, lk, hkv, d, dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

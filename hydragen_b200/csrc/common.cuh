@@ -1,0 +1,181 @@
+// Shared device/host helpers for the hydragen_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hydragen_b200.h"
+
+namespace hg {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// ---- error plumbing (api.cu) ------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);
+struct DeviceInfo {
+  bool ready = false;
+  int device = -1;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime
+};
+const DeviceInfo& device_info();
+
+// ---- 16-byte vector of T <-> fp32 --------------------------------------------------------
+template <typename T>
+struct Vec16;  // VEC elements of T in one 128-bit word
+
+template <>
+struct Vec16<float> {
+  static constexpr int VEC = 4;
+  static __device__ __forceinline__ void unpack(const uint4& u, float* f) {
+    f[0] = __uint_as_float(u.x);
+    f[1] = __uint_as_float(u.y);
+    f[2] = __uint_as_float(u.z);
+    f[3] = __uint_as_float(u.w);
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+};
+
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  // bf16 -> fp32 is a 16-bit shift: two ALU ops per packed pair, no conversion unit.
+  static __device__ __forceinline__ void unpack(const uint4& u, float* f) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <>
+struct Vec16<__half> {
+  static constexpr int VEC = 8;
+  static __device__ __forceinline__ void unpack(const uint4& u, float* f) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T x);
+template <>
+__device__ __forceinline__ float to_f32<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half x) { return __half2float(x); }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float x);
+template <>
+__device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float x) { return __float2half_rn(x); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// Streaming 128-bit load: read-only path, do not allocate in L1 (each K/V row is used once).
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ld_v4(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st_v4(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_log2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Pointer tables passed by value (copied from the caller's host arrays at launch).
+struct PartialTable {
+  const void* outs[HG_MAX_COMBINE];
+  const float* lses[HG_MAX_COMBINE];
+  int n;
+};
+
+// ---- launchers implemented in the .cu files ---------------------------------------------
+int launch_combine(const PartialTable& t, void* out, float* lse_out, int64_t rows, int d, int dtype, cudaStream_t s);
+
+struct RowwiseParams {
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* seq_lens;
+  int seq_lens_i64;
+  const int32_t* cu_seqlens_k;
+  int kv_group_size;
+  int causal;
+  void* out;
+  float* lse;
+  int b, nq, lk, hq, hkv, d;
+  int64_t q_stride_b, q_stride_s, q_stride_h;
+  int64_t kv_stride_b, kv_stride_s, kv_stride_h;
+  PartialTable partials;
+  float scale_log2;  // sm_scale * log2(e)
+};
+int launch_rowwise(const RowwiseParams& p, int dtype, cudaStream_t s);
+
+struct PrefixParams {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  float* lse;
+  int n_groups, q_per_group;
+  int64_t n_k_rows;
+  int k_len;
+  const int32_t* cu_seqlens_k;
+  int max_k_len;
+  int hq, hkv, d;
+  int64_t q_stride_row, kv_stride_row;
+  float scale_log2;
+};
+int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s);
+
+int launch_kv_append(const void* k_new, const void* v_new, const void* positions, int positions_i64, void* k_cache,
+                     void* v_cache, int b, int nq, int lk, int hkv, int d, int dtype, cudaStream_t s);
+
+}  // namespace hg

@@ -1,0 +1,521 @@
+// Shared-prefix attention on the Blackwell tensor cores: tcgen05.mma + TMEM + TMA (sm_100a).
+//
+// Replaces the reference's prefix branch -- hydragen/attention.py:261-338 calling
+// flash_attention / flash_attention_varlen (hydragen/flash.py:284-351), i.e. flash-attn v2.3.6's
+// mma.sync (Ampere) kernel, plus the LSE transposes of attention.py:276-280,333-338.
+//
+// Inter-sequence batching makes this a dense problem: for one (group, head) the queries of every
+// sequence sharing the prefix form Q[q_per_group x d] and are multiplied against the single
+// K,V[k_len x d] of that prefix.  One CTA owns a 128-row Q tile of one head and streams the
+// prefix in 128-key blocks:
+//
+//   warp 0 (1 lane)  TMA producer: Q once, then K_j / V_j into 2-deep smem rings
+//                    (cp.async.bulk.tensor, SWIZZLE_128B boxes of 128 rows x 64 elements)
+//   warp 1 (1 lane)  MMA issuer:   S_j = Q K_j^T  (SS form, both operands K-major in smem,
+//                                  128x128x16 per instruction, fp32 accumulate in TMEM)
+//                                  O += P_j V_j   (TS form: P_j read from TMEM as the A operand,
+//                                  V_j straight from its row-major smem tile as an MN-major B
+//                                  operand -- no transpose pass)
+//   warp 2           TMEM allocator (512 columns: S0 | S1 | O)
+//   warps 4-7        softmax: thread t owns row t (tcgen05.ld 32x32b: lane == row, so the row
+//                    max / row sum need no shuffles), exp2 with the scale folded into one FFMA,
+//                    P_j written back over S_j in TMEM as packed 16-bit, lazy rescale of O
+//                    (only when the running max grows by more than 2^8), epilogue O / l -> gmem,
+//                    LSE written directly in [b, nq, hq].
+//
+// S is double buffered so that Q K_{j+1}^T runs on the tensor pipe while the softmax warps work
+// on S_j.  All producer/consumer edges are mbarriers (TMA complete_tx, tcgen05.commit, thread
+// arrives); there is no __syncthreads in the main loop.
+//
+// Algorithmic work per CTA tile: 4 * 128 * k_len * d FLOP.  Bound: tensor pipe (AI ~ 680 FLOP/B
+// at the 7B config), with the MUFU exp2 rate (16/clk/SM == the 128x128x128 MMA rate) the
+// co-limiter.
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace hg {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 128;
+constexpr int kThreads = 256;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemS0 = 0, kTmemS1 = 128, kTmemO = 256;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// tcgen05.commit: the mbarrier gets one arrival when every MMA issued so far by this thread is done.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 UMMA): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout [61,64) with SWIZZLE_128B = 2.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor, kind::f16: D fmt [4,6) (1 = f32) | A fmt [7,10) | B fmt [10,13) (0 = f16, 1 = bf16) |
+// A major bit 15 | B major bit 16 (0 = K-major, 1 = MN-major) | N>>3 [17,23) | M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int b_mn_major, int m, int n) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+#define HG_R32(a, o)                                                                                                    \
+  "=r"(a[o + 0]), "=r"(a[o + 1]), "=r"(a[o + 2]), "=r"(a[o + 3]), "=r"(a[o + 4]), "=r"(a[o + 5]), "=r"(a[o + 6]),        \
+      "=r"(a[o + 7]), "=r"(a[o + 8]), "=r"(a[o + 9]), "=r"(a[o + 10]), "=r"(a[o + 11]), "=r"(a[o + 12]), "=r"(a[o + 13]), \
+      "=r"(a[o + 14]), "=r"(a[o + 15]), "=r"(a[o + 16]), "=r"(a[o + 17]), "=r"(a[o + 18]), "=r"(a[o + 19]),               \
+      "=r"(a[o + 20]), "=r"(a[o + 21]), "=r"(a[o + 22]), "=r"(a[o + 23]), "=r"(a[o + 24]), "=r"(a[o + 25]),               \
+      "=r"(a[o + 26]), "=r"(a[o + 27]), "=r"(a[o + 28]), "=r"(a[o + 29]), "=r"(a[o + 30]), "=r"(a[o + 31])
+#define HG_W32(a, o)                                                                                                     \
+  "r"(a[o + 0]), "r"(a[o + 1]), "r"(a[o + 2]), "r"(a[o + 3]), "r"(a[o + 4]), "r"(a[o + 5]), "r"(a[o + 6]), "r"(a[o + 7]), \
+      "r"(a[o + 8]), "r"(a[o + 9]), "r"(a[o + 10]), "r"(a[o + 11]), "r"(a[o + 12]), "r"(a[o + 13]), "r"(a[o + 14]),       \
+      "r"(a[o + 15]), "r"(a[o + 16]), "r"(a[o + 17]), "r"(a[o + 18]), "r"(a[o + 19]), "r"(a[o + 20]), "r"(a[o + 21]),     \
+      "r"(a[o + 22]), "r"(a[o + 23]), "r"(a[o + 24]), "r"(a[o + 25]), "r"(a[o + 26]), "r"(a[o + 27]), "r"(a[o + 28]),     \
+      "r"(a[o + 29]), "r"(a[o + 30]), "r"(a[o + 31])
+
+// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp gets lane (warp%4)*32 + t.
+#define HG_TMEM_LD32(taddr, a, o)                                                                               \
+  asm volatile(                                                                                                 \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                 \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27," \
+      "%28,%29,%30,%31}, [%32];"                                                                                \
+      : HG_R32(a, o)                                                                                            \
+      : "r"(taddr))
+#define HG_TMEM_ST32(taddr, a, o)                                                                               \
+  asm volatile(                                                                                                 \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "                                                          \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27," \
+      "%28,%29,%30,%31};" ::HG_W32(a, o),                                                                       \
+      "r"(taddr)                                                                                                \
+      : "memory")
+
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));  // first source -> upper half
+  return r;
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+template <int D>
+struct SmemLayout {
+  static constexpr int kHalves = D / 64;                 // 64-element (128-byte) swizzle atoms along d
+  static constexpr int kTileBytes = BLOCK_N * D * 2;     // one Q / K / V tile
+  static constexpr int kHalfBytes = BLOCK_N * 64 * 2;    // one TMA box: 128 rows x 128 B
+  static constexpr int kQ = 0;
+  static constexpr int kK = kTileBytes;                  // 2 stages
+  static constexpr int kV = kTileBytes * 3;              // 2 stages
+  static constexpr int kBars = kTileBytes * 5;
+  static constexpr int kTotal = kBars + 256;
+};
+
+struct Barriers {
+  uint64_t q_full;
+  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
+  uint64_t s_full[2], p_full[2];
+  uint64_t pv_done;
+  uint32_t tmem_base;
+};
+
+}  // namespace
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads, 1)
+    prefix_attn_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                             const __grid_constant__ CUtensorMap tmap_v, T* __restrict__ out, float* __restrict__ lse,
+                             const int32_t* __restrict__ cu_seqlens_k, int q_per_group, int tiles_per_group, int k_len_uniform,
+                             int hq, int hkv, float scale_log2) {
+  using L = SmemLayout<D>;
+  constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+  constexpr uint32_t kIdescQK = make_idesc(kFmt, 0, BLOCK_M, BLOCK_N);
+  constexpr uint32_t kIdescPV = make_idesc(kFmt, 1, BLOCK_M, D);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + L::kBars);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, head = blockIdx.y;
+  const int grp = tile / tiles_per_group, mt = tile % tiles_per_group;
+  const int kvh = head / (hq / hkv);
+  const int q_row0 = grp * q_per_group + mt * BLOCK_M;
+  const int rows_valid = min(BLOCK_M, q_per_group - mt * BLOCK_M);
+  int k_start, k_len;
+  if (cu_seqlens_k != nullptr) {
+    k_start = __ldg(cu_seqlens_k + grp);
+    k_len = __ldg(cu_seqlens_k + grp + 1) - k_start;
+  } else {
+    k_start = grp * k_len_uniform;
+    k_len = k_len_uniform;
+  }
+  const int n_blocks = (k_len + BLOCK_N - 1) / BLOCK_N;
+
+  if (n_blocks == 0) {  // empty prefix: out = 0, lse = -inf (uniform branch for the whole CTA)
+    for (int idx = threadIdx.x; idx < rows_valid * (D / 8); idx += kThreads) {
+      const int r = idx / (D / 8), c = idx % (D / 8);
+      st_v4(out + ((int64_t)(q_row0 + r) * hq + head) * D + c * 8, make_uint4(0, 0, 0, 0));
+    }
+    if (lse != nullptr)
+      for (int r = threadIdx.x; r < rows_valid; r += kThreads) lse[(int64_t)(q_row0 + r) * hq + head] = -INFINITY;
+    return;
+  }
+
+  // ---- one-time setup --------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_v) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bars->q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->k_full[i], 1);
+      mbar_init(&bars->k_empty[i], 1);
+      mbar_init(&bars->v_full[i], 1);
+      mbar_init(&bars->v_empty[i], 1);
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->p_full[i], 128);
+    }
+    mbar_init(&bars->pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_base);
+
+  if (warp == 0) {
+    // =============================== TMA producer ===========================================
+    if (lane == 0) {
+      mbar_expect_tx(&bars->q_full, L::kTileBytes);
+#pragma unroll
+      for (int h = 0; h < L::kHalves; ++h)
+        tma_load_2d(smem + L::kQ + h * L::kHalfBytes, &tmap_q, head * D + h * 64, q_row0, &bars->q_full);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int row = k_start + j * BLOCK_N;
+        mbar_wait(&bars->k_empty[st], ph ^ 1);
+        mbar_expect_tx(&bars->k_full[st], L::kTileBytes);
+#pragma unroll
+        for (int h = 0; h < L::kHalves; ++h)
+          tma_load_2d(smem + L::kK + st * L::kTileBytes + h * L::kHalfBytes, &tmap_k, kvh * D + h * 64, row, &bars->k_full[st]);
+        mbar_wait(&bars->v_empty[st], ph ^ 1);
+        mbar_expect_tx(&bars->v_full[st], L::kTileBytes);
+#pragma unroll
+        for (int h = 0; h < L::kHalves; ++h)
+          tma_load_2d(smem + L::kV + st * L::kTileBytes + h * L::kHalfBytes, &tmap_v, kvh * D + h * 64, row, &bars->v_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =============================================
+    if (lane == 0) {
+      const uint32_t q_addr = smem_u32(smem + L::kQ);
+      // S = Q K^T: D/16 instructions of 128x128x16; operand k-slice kk lives in swizzle atom kk/4
+      // at byte offset (kk%4)*32 inside the 128-byte row.
+      auto issue_qk = [&](int st, uint32_t s_col) {
+        const uint32_t k_addr = smem_u32(smem + L::kK + st * L::kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk / 4) * L::kHalfBytes + (kk % 4) * 32;
+          umma_ss(tmem + s_col, make_smem_desc(q_addr + off, 0, 1024), make_smem_desc(k_addr + off, 0, 1024), kIdescQK,
+                  kk > 0 ? 1u : 0u);
+        }
+      };
+      // O (+)= P V: BLOCK_N/16 instructions of 128xDx16; A = P (16-bit, 8 TMEM columns per k-slice),
+      // B = V tile rows [kk*16, kk*16+16) as an MN-major operand: 8-row groups 1024 B apart (SBO),
+      // 64-element column halves one TMA box apart (LBO).
+      auto issue_pv = [&](int st, uint32_t p_col, bool first) {
+        const uint32_t v_addr = smem_u32(smem + L::kV + st * L::kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < BLOCK_N / 16; ++kk) {
+          umma_ts(tmem + kTmemO, tmem + p_col + kk * 8, make_smem_desc(v_addr + kk * 2048, L::kHalfBytes, 1024), kIdescPV,
+                  (first && kk == 0) ? 0u : 1u);
+        }
+      };
+
+      mbar_wait(&bars->q_full, 0);
+      mbar_wait(&bars->k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, kTmemS0);
+      umma_commit(&bars->k_empty[0]);
+      umma_commit(&bars->s_full[0]);
+      for (int j = 0; j < n_blocks; ++j) {
+        if (j + 1 < n_blocks) {
+          const int st = (j + 1) & 1;
+          mbar_wait(&bars->k_full[st], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_qk(st, st ? kTmemS1 : kTmemS0);
+          umma_commit(&bars->k_empty[st]);
+          umma_commit(&bars->s_full[st]);
+        }
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&bars->p_full[st], ph);
+        mbar_wait(&bars->v_full[st], ph);
+        tc_fence_after();
+        issue_pv(st, st ? kTmemS1 : kTmemS0, j == 0);
+        umma_commit(&bars->v_empty[st]);
+        umma_commit(&bars->pv_done);
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== softmax / correction / epilogue ==========================
+    const int wq = warp - 4;           // == warp % 4: the TMEM lane quarter this warp may access
+    const int row = wq * 32 + lane;    // row of the tile == TMEM lane
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    float m_used = -INFINITY;          // raw-score max the exponentials are referenced to
+    float l = 0.f;
+
+    for (int j = 0; j < n_blocks; ++j) {
+      const int buf = j & 1;
+      const uint32_t s_addr = tmem + lane_base + (buf ? kTmemS1 : kTmemS0);
+      mbar_wait(&bars->s_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sr[128];
+      HG_TMEM_LD32(s_addr + 0, sr, 0);
+      HG_TMEM_LD32(s_addr + 32, sr, 32);
+      HG_TMEM_LD32(s_addr + 64, sr, 64);
+      HG_TMEM_LD32(s_addr + 96, sr, 96);
+      tmem_wait_ld();
+
+      const int rem = k_len - j * BLOCK_N;  // valid keys in this block
+      if (rem < BLOCK_N) {
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (c >= rem) sr[c] = 0xff800000u;  // -inf
+      }
+      float m_blk = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; ++c) m_blk = fmaxf(m_blk, __uint_as_float(sr[c]));
+      const float m_new = fmaxf(m_used, m_blk);
+      if (j == 0) {
+        m_used = m_new;
+      } else {
+        const bool need = (m_new - m_used) * scale_log2 > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // O must be complete (P_{j-1} V_{j-1} done) before it is rescaled in place.
+          mbar_wait(&bars->pv_done, (j - 1) & 1);
+          tc_fence_after();
+          const float alpha = need ? fast_exp2((m_used - m_new) * scale_log2) : 1.f;
+          if (need) {
+            m_used = m_new;
+            l *= alpha;
+          }
+#pragma unroll
+          for (int c0 = 0; c0 < D; c0 += 32) {
+            uint32_t o[32];
+            HG_TMEM_LD32(tmem + lane_base + kTmemO + c0, o, 0);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            HG_TMEM_ST32(tmem + lane_base + kTmemO + c0, o, 0);
+          }
+        }
+      }
+      const float neg_mc = -m_used * scale_log2;
+      float psum = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 128; c += 2) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c]), scale_log2, neg_mc));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + 1]), scale_log2, neg_mc));
+        psum += p0 + p1;
+        pk[c / 2] = pack2<T>(p0, p1);
+      }
+      l += psum;
+      HG_TMEM_ST32(s_addr + 0, pk, 0);
+      HG_TMEM_ST32(s_addr + 32, pk, 32);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars->p_full[buf]);
+    }
+
+    // ---- epilogue --------------------------------------------------------------------------
+    mbar_wait(&bars->pv_done, (n_blocks - 1) & 1);
+    tc_fence_after();
+    const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+    const bool row_ok = row < rows_valid;
+    T* orow = out + ((int64_t)(q_row0 + row) * hq + head) * D;
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t o[32];
+      HG_TMEM_LD32(tmem + lane_base + kTmemO + c0, o, 0);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 w;
+          w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+          w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+          w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+          w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+          st_v4(orow + c0 + c, w);
+        }
+      }
+    }
+    if (row_ok && lse != nullptr)
+      lse[(int64_t)(q_row0 + row) * hq + head] = (l > 0.f) ? (m_used * scale_log2 + fast_log2(l)) * kLn2 : -INFINITY;
+    tc_fence_before();
+  }
+
+  // ---- teardown ----------------------------------------------------------------------------
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D view [rows, cols] of a 16-bit tensor with row stride `row_stride` elements; boxes of 128 rows x 64 cols,
+// SWIZZLE_128B (a box row is exactly one 128-byte swizzle span), rows past `rows` read as zero.
+static int make_tmap(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t row_stride) {
+  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(device_info().encode_tiled);
+  if (fn == nullptr) return set_error(HG_ERR_NOT_INITIALIZED, "prefix: cuTensorMapEncodeTiled unavailable (call hg_init first)");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {row_stride * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dtype == HG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(HG_ERR_CUDA, "prefix: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return HG_OK;
+}
+
+template <typename T, int D>
+static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) {
+  using L = SmemLayout<D>;
+  const int64_t n_q_rows = (int64_t)p.n_groups * p.q_per_group;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap(&tq, p.q, dtype, n_q_rows, (uint64_t)p.hq * D, p.q_stride_row)) != HG_OK) return rc;
+  if ((rc = make_tmap(&tk, p.k, dtype, p.n_k_rows, (uint64_t)p.hkv * D, p.kv_stride_row)) != HG_OK) return rc;
+  if ((rc = make_tmap(&tv, p.v, dtype, p.n_k_rows, (uint64_t)p.hkv * D, p.kv_stride_row)) != HG_OK) return rc;
+  const int smem_bytes = L::kTotal + 1024;
+  static bool attr_set = false;  // per instantiation; idempotent, racing threads set the same value
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(prefix_attn_sm100_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return set_error(HG_ERR_CUDA, "prefix: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles_per_group = (p.q_per_group + BLOCK_M - 1) / BLOCK_M;
+  dim3 grid((unsigned)(p.n_groups * tiles_per_group), (unsigned)p.hq, 1);
+  prefix_attn_sm100_kernel<T, D><<<grid, kThreads, smem_bytes, s>>>(tq, tk, tv, (T*)p.out, p.lse, p.cu_seqlens_k, p.q_per_group,
+                                                                     tiles_per_group, p.k_len, p.hq, p.hkv, p.scale_log2);
+  return check_launch("prefix_attn_sm100");
+}
+
+int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
+  if (p.n_groups == 0 || p.q_per_group == 0) return HG_OK;
+  if (dtype != HG_F16 && dtype != HG_BF16)
+    return set_error(HG_ERR_UNSUPPORTED, "prefix: the tcgen05 kernel takes f16/bf16 only (dtype %d)", dtype);
+  if (p.q_stride_row % 8 != 0 || p.kv_stride_row % 8 != 0 || reinterpret_cast<uintptr_t>(p.q) % 16 != 0 ||
+      reinterpret_cast<uintptr_t>(p.k) % 16 != 0 || reinterpret_cast<uintptr_t>(p.v) % 16 != 0 ||
+      reinterpret_cast<uintptr_t>(p.out) % 16 != 0)
+    return set_error(HG_ERR_UNSUPPORTED, "prefix: TMA needs 16-byte aligned bases and row strides");
+  if (p.hq > 65535) return set_error(HG_ERR_UNSUPPORTED, "prefix: hq > 65535");
+  if (dtype == HG_BF16) {
+    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64>(p, dtype, s);
+  } else {
+    if (p.d == 128) return launch_prefix_inst<__half, 128>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__half, 64>(p, dtype, s);
+  }
+  return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
+}
+
+}  // namespace hg

@@ -1,0 +1,212 @@
+"""Attention primitives returning ``(out, lse)`` -- the surface of the reference's
+``hydragen/flash.py`` (same names, argument meaning and return layouts), implemented by the
+hand-written sm_100a kernels behind the C ABI.  No flash-attn, no Triton, no CPU fallback.
+
+=====================================  =======================================================
+reference (hydragen/flash.py)          here
+=====================================  =======================================================
+``flash_attention`` :284-306           tcgen05 prefix kernel (non-causal, 16-bit, d in {64,128});
+  (flash-attn _flash_attn_forward)     row-wise kernel otherwise (causal / fp32)
+``flash_attention_varlen`` :309-351    tcgen05 prefix kernel with a device ``cu_seqlens_k`` table
+``flash_attention_seqlen`` :163-281    row-wise kernel (one launch instead of cast + split-K +
+  (+ Triton kernels, pick_split_k)     reduce); warps-per-sequence chosen from the cache length
+=====================================  =======================================================
+
+LSE convention (all): fp32 natural log of sum exp(q.k / sqrt(d)).  ``flash_attention`` /
+``flash_attention_varlen`` return it shaped ``[b, h, sq]`` like flash-attn v2.3.6 does -- as a
+permuted VIEW of the ``[b, sq, h]`` buffer the kernels write, so the reference's
+``rearrange(...).contiguous()`` on it is a no-op instead of a transpose pass.
+"""
+
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+_TC_DTYPES = (torch.float16, torch.bfloat16)
+_TC_HEAD_DIMS = (64, 128)
+
+
+def _prefix_backend() -> str:
+    """'auto' (default), 'tcgen05' or 'rowwise' -- test hook, read per call."""
+    return os.environ.get("HYDRAGEN_B200_PREFIX_BACKEND", "auto")
+
+
+def _rows_view(t: Tensor) -> Optional[int]:
+    """Row stride (elements) if the (b, s) axes of a [b, s, h, d] tensor collapse into one row axis
+    with a uniform stride and each row is a dense [h, d] block; None otherwise."""
+    b, s, h, d = t.shape
+    if t.stride(3) != 1 or (h > 1 and t.stride(2) != d):
+        return None
+    if s == 1:
+        rs = t.stride(0) if b > 1 else h * d
+    elif b == 1:
+        rs = t.stride(1)
+    else:
+        if t.stride(0) != s * t.stride(1):
+            return None
+        rs = t.stride(1)
+    return rs if rs >= h * d else None
+
+
+def _inner_ok(t: Tensor) -> bool:
+    return t.stride(-1) == 1
+
+
+def _check_qkv(q: Tensor, k: Tensor, v: Tensor):
+    if q.ndim != 4 or k.ndim != 4 or v.ndim != 4:
+        raise ValueError(f"expected 4-d q/k/v, got {tuple(q.shape)} {tuple(k.shape)} {tuple(v.shape)}")
+    if k.shape != v.shape:
+        raise ValueError(f"k/v shape mismatch {tuple(k.shape)} {tuple(v.shape)}")
+    if q.shape[-1] != k.shape[-1]:
+        raise ValueError(f"Keys have head dim {k.shape[-1]} but queries have head dim {q.shape[-1]}")
+    if q.dtype != k.dtype or q.dtype != v.dtype:
+        raise ValueError("q/k/v dtypes differ")
+    if q.shape[2] % k.shape[2] != 0:
+        raise ValueError(f"qheads {q.shape[2]} must be a multiple of kvheads {k.shape[2]}")
+
+
+def prefix_attention_grouped(
+    q: Tensor,
+    k: Tensor,
+    v: Tensor,
+    n_groups: int,
+    cu_seqlens_k: Optional[Tensor] = None,
+    max_seqlen_k: Optional[int] = None,
+) -> Tuple[Tensor, Tensor]:
+    """The prefix branch proper: ``q [b, nq, hq, d]`` with the batch grouped contiguously by shared
+    parent (``b % n_groups == 0``), ``k, v`` either ``[n_groups, L, hkv, d]`` or, with
+    ``cu_seqlens_k`` (int32 ``[n_groups + 1]`` on device), packed ``[total, hkv, d]``.
+    Returns ``out [b, nq, hq, d]`` and ``lse [b, nq, hq]`` (fp32) -- already in the layout the
+    combine consumes (hydragen/attention.py:276-280, 333-338 need no transpose here)."""
+    b, nq, hq, d = q.shape
+    if n_groups < 1 or b % n_groups != 0:
+        raise ValueError(f"batch {b} is not a multiple of the number of shared sequences {n_groups}")
+    hkv = k.shape[-2]
+    sm_scale = d**-0.5  # hydragen/flash.py:293
+    out = torch.empty((b, nq, hq, d), device=q.device, dtype=q.dtype)
+    lse = torch.empty((b, nq, hq), device=q.device, dtype=torch.float32)
+    backend = _prefix_backend()
+    use_tc = q.dtype in _TC_DTYPES and d in _TC_HEAD_DIMS and backend != "rowwise"
+    if backend == "tcgen05" and not use_tc:
+        raise ValueError(f"tcgen05 prefix kernel does not take dtype {q.dtype} / head_dim {d}")
+    varlen = cu_seqlens_k is not None
+    if varlen:
+        if k.ndim != 3:
+            raise ValueError("varlen shared K/V must be [total, kvheads, d]")
+        if cu_seqlens_k.dtype != torch.int32 or cu_seqlens_k.shape[0] != n_groups + 1:
+            raise ValueError("cu_seqlens_k must be int32 of n_groups + 1 entries")
+    if use_tc:
+        q_rs = _rows_view(q)
+        if q_rs is None:
+            q = q.contiguous()
+            q_rs = hq * d
+        if varlen:
+            if not (k.stride(2) == 1 and k.stride(1) == d and v.stride() == k.stride()):
+                k, v = k.contiguous(), v.contiguous()
+            n_k_rows, k_len, kv_rs = k.shape[0], 0, k.stride(0)
+            max_k = int(max_seqlen_k) if max_seqlen_k is not None else k.shape[0]
+        else:
+            if k.ndim != 4 or k.shape[0] != n_groups:
+                raise ValueError(f"shared K/V must be [n_groups, L, kvheads, d], got {tuple(k.shape)}")
+            kv_rs = _rows_view(k)
+            if kv_rs is None or _rows_view(v) != kv_rs:
+                k, v = k.contiguous(), v.contiguous()
+                kv_rs = hkv * d
+            n_k_rows, k_len = k.shape[0] * k.shape[1], k.shape[1]
+            max_k = k_len
+        _lib.prefix_attn_fwd(q, k, v, out, lse, n_groups, (b // n_groups) * nq, n_k_rows, k_len, cu_seqlens_k, max_k,
+                             hq, hkv, d, q_rs, kv_rs, sm_scale)
+    else:
+        # CUDA-core path (fp32, other head dims): every sequence walks its parent's keys.
+        if not _inner_ok(q):
+            q = q.contiguous()
+        if not _inner_ok(k):
+            k = k.contiguous()
+        if not _inner_ok(v) or v.stride() != k.stride():
+            v = v.contiguous()
+            k = k.contiguous()
+        if varlen:
+            strides = (0, k.stride(0), k.stride(1))
+            lk = int(max_seqlen_k) if max_seqlen_k is not None else k.shape[0]
+        else:
+            strides = (k.stride(0), k.stride(1), k.stride(2))
+            lk = k.shape[1]
+        _lib.rowwise_attn_fwd(q, k, v, None, cu_seqlens_k, b // n_groups, False, out, lse, lk, strides, [], [], sm_scale)
+    return out, lse
+
+
+def flash_attention(q: Tensor, k: Tensor, v: Tensor, causal: bool = False) -> Tuple[Tensor, Tensor]:
+    """hydragen/flash.py:284-306.  q [b, sq, hq, d]; k, v [b, sk, hkv, d] -> out [b, sq, hq, d],
+    lse [b, hq, sq] (fp32).  ``causal`` is bottom-right aligned when sq != sk (flash-attn >= 2.1)."""
+    _check_qkv(q, k, v)
+    b, sq, hq, d = q.shape
+    if not causal:
+        out, lse = prefix_attention_grouped(q, k, v, n_groups=b)
+        return out, lse.permute(0, 2, 1)
+    out, lse = _rowwise(q, k, v, None, causal=True)
+    return out, lse.permute(0, 2, 1)
+
+
+def flash_attention_varlen(
+    q: Tensor,
+    k: Tensor,
+    v: Tensor,
+    cu_seqlens_q: Tensor,
+    cu_seqlens_k: Tensor,
+    max_seqlen_q: int,
+    max_seqlen_k: int,
+    causal: bool = False,
+) -> Tuple[Tensor, Tensor]:
+    """hydragen/flash.py:309-351.  q [total_q, hq, d], k/v [total_k, hkv, d]; returns
+    out [total_q, hq, d] and lse [n, hq, max_seqlen_q] (the flash-attn v2.3.6 layout).
+
+    As in every call the reference makes (hydragen/attention.py:295-321), all n query groups must
+    hold exactly ``max_seqlen_q`` rows (checked without a device sync: n * max_seqlen_q ==
+    total_q); the key side is ragged and read from ``cu_seqlens_k`` on the device."""
+    if causal:
+        raise NotImplementedError("flash_attention_varlen(causal=True) is never used on the Hydragen path")
+    if q.ndim != 3 or k.ndim != 3 or v.ndim != 3:
+        raise ValueError("varlen tensors must be [total, heads, d]")
+    n = cu_seqlens_q.shape[0] - 1
+    total_q, hq, d = q.shape
+    if n * max_seqlen_q != total_q:
+        raise NotImplementedError("ragged query groups are not supported (the Hydragen path never produces them)")
+    out, lse = prefix_attention_grouped(q.view(n, max_seqlen_q, hq, d) if q.is_contiguous() else q.reshape(n, max_seqlen_q, hq, d),
+                                        k, v, n_groups=n, cu_seqlens_k=cu_seqlens_k, max_seqlen_k=max_seqlen_k)
+    return out.view(total_q, hq, d), lse.view(n, max_seqlen_q, hq).permute(0, 2, 1)
+
+
+def _rowwise(q, k, v, seq_len, causal, partial_outs=(), partial_lses=()):
+    b, nq, hq, d = q.shape
+    if not _inner_ok(q):
+        q = q.contiguous()
+    if not _inner_ok(k):
+        k = k.contiguous()
+    if not _inner_ok(v) or v.stride() != k.stride():
+        v = v.contiguous()
+        k = k.contiguous()
+    out = torch.empty((b, nq, hq, d), device=q.device, dtype=q.dtype)
+    lse = torch.empty((b, nq, hq), device=q.device, dtype=torch.float32)
+    _lib.rowwise_attn_fwd(q, k, v, seq_len, None, 1, causal, out, lse, k.shape[1],
+                          (k.stride(0), k.stride(1), k.stride(2)), list(partial_outs), list(partial_lses), d**-0.5)
+    return out, lse
+
+
+def flash_attention_seqlen(raw_q: Tensor, raw_k: Tensor, raw_v: Tensor, seq_len: Optional[Tensor] = None):
+    """hydragen/flash.py:163-281.  q [b, q, hq, d]; k, v [b, kmax, hkv, d]; sequence b attends to
+    keys < seq_len[b] (int32 or int64, on device; no causal mask).  Returns out [b, q, hq, d] and
+    lse [b, q, hq] fp32.  (``seq_len=None`` crashes in the reference; here it means "all keys".)"""
+    _check_qkv(raw_q, raw_k, raw_v)
+    return _rowwise(raw_q, raw_k, raw_v, seq_len, causal=False)
+
+
+def suffix_attention_fused(q, k, v, seq_len, causal, partial_outs, partial_lses):
+    """Suffix branch + combine in one launch (hydragen/attention.py:343-352): the per-sequence
+    result is merged in registers with the prefix partials; returns (final out, merged lse)."""
+    return _rowwise(q, k, v, seq_len, causal, partial_outs, partial_lses)

@@ -1,0 +1,156 @@
+/*
+ * hydragen_b200 -- C ABI of the B200 (sm_100a) shared-prefix attention hot path.
+ *
+ * The reference (ScalingIntelligence/hydragen) has no FFI layer: its hot path is a set of
+ * Python functions that call flash-attn's CUDA extension and three Triton kernels.  Each entry
+ * point below replaces one of those calls; the Python shim in hydragen_b200/{attention,flash}.py
+ * keeps the reference signatures and binds these symbols with ctypes (see INTEGRATION.md for the
+ * stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in
+ *     `_host` ; the library never allocates, frees or retains device memory (the caller owns
+ *     outputs and workspace) and never synchronises: all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), so every entry point is CUDA-graph capturable.
+ *   - return value: 0 on success, negative hg_status otherwise; hg_last_error() returns a
+ *     thread-local message.  No C++ exception crosses the boundary.
+ *   - strides are in ELEMENTS of the tensor's dtype; the innermost (head_dim) stride is 1.
+ *   - log-sum-exp tensors are fp32, natural log of sum exp(scale * q.k), laid out [b, nq, hq]
+ *     (row = b*nq + qi, then head) -- the layout the reference's combine consumes
+ *     (hydragen/attention.py:110-126), so no transpose pass is ever needed.
+ *   - a query row with no valid key yields out = 0 and lse = -inf.
+ */
+#ifndef HYDRAGEN_B200_H_
+#define HYDRAGEN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_ABI_VERSION 1
+#define HG_MAX_COMBINE 8 /* max partial results merged by one call (shared levels + suffix) */
+
+typedef enum hg_dtype {
+  HG_F16 = 0,
+  HG_BF16 = 1,
+  HG_F32 = 2 /* CUDA-core kernels only (combine, rowwise attention); not the tcgen05 prefix kernel */
+} hg_dtype;
+
+typedef enum hg_status {
+  HG_OK = 0,
+  HG_ERR_INVALID_ARGUMENT = -1,
+  HG_ERR_UNSUPPORTED = -2, /* valid request the kernels do not cover (e.g. head_dim) */
+  HG_ERR_CUDA = -3,        /* launch / driver error; message holds cudaGetErrorString */
+  HG_ERR_NOT_INITIALIZED = -4
+} hg_status;
+
+/* ABI version of the loaded library (== HG_ABI_VERSION). */
+int hg_abi_version(void);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* hg_last_error(void);
+
+/* Query the device once (SM count, shared memory, driver entry point for TMA descriptors).
+ * Must be called once per process after the CUDA context of `device` exists and BEFORE any
+ * stream capture; later calls are no-ops.  Replaces the per-call
+ * torch.cuda.get_device_properties of hydragen/flash.py:193. */
+int hg_init(int device);
+
+/* Number of SMs seen by hg_init (0 before). */
+int hg_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * combine: out = sum_i w_i * outs[i] / sum_i w_i,  w_i = exp(lses[i] - max_i lses[i])
+ * Replaces combine_lse / combine_lse_triton / combine_lse_torch (hydragen/attention.py:21-174)
+ * for ANY n in [1, HG_MAX_COMBINE] (the reference's kernel handles n == 2 only and falls back
+ * to eager torch otherwise, attention.py:169-174) and any head_dim.
+ *   outs_host[i] : [rows, d] contiguous, dtype `dtype`   (rows = b * nq * hq)
+ *   lses_host[i] : [rows] fp32
+ *   out          : [rows, d] dtype `dtype`
+ *   lse_out      : [rows] fp32 merged log-sum-exp, or NULL
+ * `outs_host` / `lses_host` are HOST arrays of n device pointers (copied into the launch).
+ */
+int hg_combine_lse(const void* const* outs_host, const float* const* lses_host, int n, void* out,
+                   float* lse_out, int64_t rows, int d, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Row-wise (CUDA-core, HBM-bound) attention: one query row against ONE sequence's own keys.
+ * This is the suffix branch of the decomposition.  Replaces
+ *   - flash_attention_seqlen  (hydragen/flash.py:163-281: Triton split-K kernel + reduce kernel +
+ *     int32 cast of seq_len), when `seq_lens` is given;
+ *   - flash_attention(q, k, v, causal=True) on per-sequence K/V (hydragen/attention.py:344),
+ *     when `seq_lens` is NULL and `causal` = 1 (bottom-right aligned, flash-attn >= 2.1);
+ * and, when n_partials > 0, ALSO the combine that follows it (attention.py:352): the suffix
+ * result is merged in registers with the already computed prefix partials and only the final
+ * output is written.
+ *
+ *   q        [b, nq, hq, d]     strides q_stride_b, q_stride_s, q_stride_h (elements)
+ *   k, v     [b_kv, lk, hkv, d] strides kv_stride_b, kv_stride_s, kv_stride_h; sequence b reads
+ *            batch entry (b / kv_group_size) -- kv_group_size = 1 for the suffix branch; > 1 lets
+ *            the same kernel serve as a (slow, exact) shared-prefix path for dtypes and head dims
+ *            the tcgen05 kernel does not take (fp32).
+ *   cu_seqlens_k  NULL, or int32 [b / kv_group_size + 1]: k, v are then packed [total, hkv, d]
+ *            (kv_stride_b ignored) and group g owns rows [cu[g], cu[g+1]) (flash-attn varlen).
+ *   seq_lens NULL, or [b] valid key counts (int32 if seq_lens_i64 == 0, else int64 -- the
+ *            reference's decode loop passes int64, hydragen/llama.py:569); keys >= seq_lens[b]
+ *            are never read (xformers_stuff.py:274-279).
+ *   causal   query qi sees keys j <= qi + (len - nq).
+ *   out      [b, nq, hq, d] contiguous, dtype `dtype`;  lse [b, nq, hq] fp32 or NULL.
+ *   partial_outs_host / partial_lses_host : HOST arrays of n_partials device pointers,
+ *            each [b, nq, hq, d] contiguous (dtype) / [b, nq, hq] fp32, merged into out/lse.
+ * d must be 64, 128 or 256 (16-bit dtypes) / 64 or 128 (fp32); hq % hkv == 0.
+ */
+int hg_rowwise_attn_fwd(const void* q, const void* k, const void* v, const void* seq_lens,
+                        int seq_lens_i64, const int32_t* cu_seqlens_k, int kv_group_size, int causal,
+                        void* out, float* lse, int b, int nq, int lk, int hq, int hkv, int d,
+                        int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
+                        int64_t kv_stride_b, int64_t kv_stride_s, int64_t kv_stride_h,
+                        const void* const* partial_outs_host, const float* const* partial_lses_host,
+                        int n_partials, float sm_scale, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Shared-prefix attention on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+ * TMEM, operands staged by TMA): all sequences that share a prefix are batched into one Q
+ * matrix per head and multiplied against the ONE copy of that prefix's K/V.
+ * Replaces flash_attention (hydragen/flash.py:284-306 -> flash-attn _flash_attn_forward, called
+ * from hydragen/attention.py:270) and flash_attention_varlen (flash.py:309-351, called from
+ * attention.py:313) together with the LSE transposes that follow them (attention.py:276-280,
+ * 333-338): the kernel writes the LSE directly in [b, nq, hq].
+ *
+ *   q      [n_q_rows, hq, d] with row stride q_stride_row (elements), rows grouped contiguously
+ *          by shared parent: group g owns rows [g*q_per_group, (g+1)*q_per_group)
+ *          (n_q_rows = n_groups * q_per_group = b * nq; the "(n s) nq -> n (s nq)" batching of
+ *          attention.py:264-268 is this view).
+ *   k, v   [n_k_rows, hkv, d] with row stride kv_stride_row; group g owns rows
+ *          [g*k_len, (g+1)*k_len) when cu_seqlens_k == NULL, else [cu[g], cu[g+1]) with
+ *          cu_seqlens_k an int32 DEVICE array of n_groups+1 entries read by the kernel (no host
+ *          sync, unlike SharedCache.fill's .item(), hydragen/llama.py:158-163) and max_k_len an
+ *          upper bound on any group's length.
+ *   out    [n_q_rows, hq, d] contiguous (dtype);  lse [n_q_rows, hq] fp32 (may be NULL).
+ * dtype HG_F16 or HG_BF16; d 64 or 128; hq % hkv == 0.  n_k_rows bounds the TMA descriptor:
+ * rows past it read as zero.
+ */
+int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
+                       int n_groups, int q_per_group, int64_t n_k_rows, int k_len,
+                       const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
+                       int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * KV-cache append for one decode step ("next" row N1 of SURVEY.md 8f): writes the new key and
+ * value row of every sequence at its own position.  Replaces the two scatter_ calls with a
+ * fully expanded int64 index in PerLayerKVCache.update_per_completion_kvs
+ * (hydragen/llama.py:236-262).
+ *   k_new, v_new [b, nq, hkv, d] contiguous;  positions [b, nq] (int32 / int64), the row of the
+ *   unique cache each new token goes to;  k_cache, v_cache [b_max, lk, hkv, d] contiguous.
+ */
+int hg_kv_append(const void* k_new, const void* v_new, const void* positions, int positions_i64,
+                 void* k_cache, void* v_cache, int b, int nq, int lk, int hkv, int d, int dtype,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDRAGEN_B200_H_ */

@@ -1,0 +1,99 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds for sm_100a, loads without a GPU
+and exports every symbol include/hydragen_b200.h declares; the Python surface mirrors the
+reference's names; the product path refuses to run without CUDA (no CPU fallback)."""
+
+import ctypes
+import inspect
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "hydragen_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hg_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(built_lib):
+    names = _declared_symbols()
+    assert {"hg_init", "hg_combine_lse", "hg_rowwise_attn_fwd", "hg_prefix_attn_fwd", "hg_kv_append", "hg_last_error"} <= set(names)
+    lib = ctypes.CDLL(built_lib)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/hydragen_b200.h but not exported"
+    lib.hg_abi_version.restype = ctypes.c_int
+    assert lib.hg_abi_version() == 1
+
+
+def test_binding_table_matches_header(built_lib):
+    from hydragen_b200 import _lib
+
+    assert sorted(_lib.SYMBOLS) == _declared_symbols()
+    _lib.load()  # binds every symbol, checks the ABI version
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma(built_lib):
+    if not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    r = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", built_lib], capture_output=True, text=True)
+    assert r.returncode == 0
+    assert "sm_100a" in r.stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG"):  # tcgen05.mma / ld / st, TMA load
+        assert mnemonic in r.stdout, mnemonic
+    assert "HMMA." not in r.stdout.replace("UTCHMMA", "")  # no legacy mma.sync path
+
+
+def test_argument_validation_without_gpu(built_lib):
+    """Invalid arguments are rejected before any CUDA call, so this runs on the CPU box."""
+    from hydragen_b200 import _lib
+
+    lib = _lib.load()
+    rc = lib.hg_combine_lse(None, None, 0, None, None, 4, 64, 0, None)
+    assert rc == -1 and b"n = 0" in lib.hg_last_error()
+    rc = lib.hg_prefix_attn_fwd(None, None, None, None, None, 1, 1, 1, 1, None, 1, 8, 8, 128, 1024, 1024, 0.1, 1, None)
+    assert rc == -4  # hg_init not called
+    args = [None] * 4 + [0, None, 1, 0, None, None, 2, 1, 4, 8, 3, 128] + [0] * 6 + [None, None, 0, 0.1, 1, None]
+    rc = lib.hg_rowwise_attn_fwd(*args)
+    assert rc == -1 and b"multiple of hkv" in lib.hg_last_error()
+
+
+def test_surface_mirrors_reference():
+    import hydragen_b200.attention as A
+    import hydragen_b200.flash as F
+
+    sig = inspect.signature(A.hydragen_attention)
+    assert list(sig.parameters) == ["q", "k", "v", "shared_ks", "shared_vs", "shared_cu_seq_lens", "shared_max_seq_lens", "use_varlens", "seq_lens"]
+    assert list(inspect.signature(A.hydragen_attention_nopad).parameters) == ["q", "k", "v", "shared_ks", "shared_vs", "seq_len"]
+    assert list(inspect.signature(A.combine_lse).parameters) == ["outs", "lses", "enable_triton"]
+    assert list(inspect.signature(F.flash_attention).parameters) == ["q", "k", "v", "causal"]
+    assert list(inspect.signature(F.flash_attention_varlen).parameters) == [
+        "q", "k", "v", "cu_seqlens_q", "cu_seqlens_k", "max_seqlen_q", "max_seqlen_k", "causal"]
+    assert list(inspect.signature(F.flash_attention_seqlen).parameters) == ["raw_q", "raw_k", "raw_v", "seq_len"]
+
+
+def test_no_cpu_fallback():
+    """CPU tensors must fail loudly: the product path never computes on the host."""
+    import hydragen_b200.attention as A
+    from hydragen_b200._lib import HydragenB200Error
+
+    q = torch.randn(2, 1, 4, 64)
+    k = torch.randn(2, 3, 4, 64)
+    sk = torch.randn(1, 5, 4, 64)
+    with pytest.raises(HydragenB200Error):
+        A.hydragen_attention_nopad(q, k, k, [sk], [sk])
+    with pytest.raises(HydragenB200Error):
+        A.combine_lse([q, q], [torch.zeros(2, 1, 4), torch.zeros(2, 1, 4)])
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "hydragen_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f"{f} mentions the oracle"

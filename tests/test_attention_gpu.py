@@ -1,0 +1,302 @@
+"""GPU parity tests (run on the B200 with ``-m gpu``): the CUDA path, called through the
+reference-shaped Python surface -> ctypes -> C ABI, against (a) the committed golden vectors made
+by the reference's own operator code, (b) the CPU oracle on the same seeded inputs, and (c) at
+BASELINE.json's full sizes, size-independent properties (decomposed == attention over the
+explicit concatenation computed by an independent kernel; two independent prefix kernels agree).
+
+Tolerances: the reference's own for fp16 -- every |diff| <= 2e-3 and mean rdiff <= 5e-3
+(tests/test_attention.py:36-38,185 of the reference); bf16 is untested upstream: 8x the fp16
+atol (3 fewer mantissa bits) = 1.6e-2 and mean rdiff <= 2e-2; fp32 1e-4 / 1e-4.
+"""
+
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+
+from oracle import hydragen_oracle as O
+import make_golden_cases as MG
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float16: (2e-3, 5e-3), torch.bfloat16: (1.6e-2, 2e-2), torch.float32: (1e-4, 1e-4)}
+DT = MG.DT
+
+
+def _dev(x, device="cuda:0"):
+    if x is None:
+        return None
+    if isinstance(x, list):
+        return [_dev(t, device) for t in x]
+    if isinstance(x, torch.Tensor):
+        return x.to(device)
+    return x
+
+
+def _assert_close(got, ref, dtype, what=""):
+    atol, rtol = TOL[dtype]
+    got = got.double().cpu()
+    ref = ref.double().cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert torch.isfinite(got).all(), what
+    ad = (got - ref).abs()
+    rd = O.rdiff(got, ref).mean().item()
+    assert ad.max().item() <= atol and rd <= rtol, f"{what}: max abs {ad.max().item():.3e} (atol {atol}), mean rdiff {rd:.3e} (rtol {rtol})"
+
+
+@pytest.fixture(autouse=True)
+def _backend_env():
+    old = os.environ.get("HYDRAGEN_B200_PREFIX_BACKEND")
+    yield
+    if old is None:
+        os.environ.pop("HYDRAGEN_B200_PREFIX_BACKEND", None)
+    else:
+        os.environ["HYDRAGEN_B200_PREFIX_BACKEND"] = old
+
+
+@pytest.mark.parametrize("backend", ["auto", "rowwise"])
+@pytest.mark.parametrize("case", MG.case_list(), ids=lambda c: c[0])
+def test_operator_matches_reference_golden(case, backend, golden):
+    """hydragen_attention on the GPU vs the golden produced by the reference's operator code."""
+    from hydragen_b200.attention import hydragen_attention
+
+    name, sizes, hq, hkv, d, dt, seed, nq = case
+    os.environ["HYDRAGEN_B200_PREFIX_BACKEND"] = backend
+    c = O.build_case(sizes, hq, hkv, d, dtype=DT[dt], seed=seed, nq=nq)
+    out = hydragen_attention(**{k: _dev(v) for k, v in c.items()})
+    torch.cuda.synchronize()
+    assert out.dtype == DT[dt] and out.shape == c["q"].shape
+    _assert_close(out, torch.from_numpy(golden[name + "/out"]), DT[dt], f"{name}/{backend}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("shape", [(1, 1, 1, 8, 8), (2, 130, 257, 8, 2), (3, 128, 128, 4, 4), (1, 300, 1000, 2, 1)])
+def test_flash_attention_tcgen05(dtype, d, shape):
+    """The prefix primitive (tcgen05) alone, out AND lse, incl. ragged tile edges
+    (q rows % 128 != 0, keys % 128 != 0) and GQA."""
+    from hydragen_b200.flash import flash_attention
+
+    os.environ["HYDRAGEN_B200_PREFIX_BACKEND"] = "tcgen05"
+    b, sq, sk, hq, hkv = shape
+    g = torch.Generator().manual_seed(b * 1000 + sq + sk + d)
+    q = torch.randn(b, sq, hq, d, generator=g).to(dtype)
+    k = torch.randn(b, sk, hkv, d, generator=g).to(dtype)
+    v = torch.randn(b, sk, hkv, d, generator=g).to(dtype)
+    out, lse = flash_attention(q.cuda(), k.cuda(), v.cuda())
+    torch.cuda.synchronize()
+    ro, rl = O.flash_attention(q, k, v)
+    assert lse.shape == (b, hq, sq) and lse.dtype == torch.float32
+    _assert_close(out, ro, dtype, "out")
+    assert (lse.double().cpu() - rl).abs().max().item() < 5e-3
+
+
+def test_flash_attention_large_scores_rescale():
+    """Forces the lazy-rescale path: the row max grows by far more than 2^8 between key blocks."""
+    from hydragen_b200.flash import flash_attention
+
+    os.environ["HYDRAGEN_B200_PREFIX_BACKEND"] = "tcgen05"
+    g = torch.Generator().manual_seed(11)
+    b, sq, sk, h, d = 1, 256, 1024, 2, 128
+    q = torch.randn(b, sq, h, d, generator=g)
+    k = torch.randn(b, sk, h, d, generator=g)
+    v = torch.randn(b, sk, h, d, generator=g)
+    # scale blocks of keys so that later blocks dominate (scores up to ~ +-60 after scaling)
+    ramp = torch.linspace(0.2, 6.0, sk).reshape(1, sk, 1, 1)
+    k = (k * ramp).to(torch.bfloat16)
+    q, v = q.to(torch.bfloat16), v.to(torch.bfloat16)
+    out, lse = flash_attention(q.cuda(), k.cuda(), v.cuda())
+    ro, rl = O.flash_attention(q, k, v)
+    _assert_close(out, ro, torch.bfloat16, "out")
+    assert (lse.double().cpu() - rl).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_flash_attention_varlen(dtype):
+    from hydragen_b200.flash import flash_attention_varlen
+
+    g = torch.Generator().manual_seed(5)
+    lens = [129, 2, 300, 64]
+    n, qps, hq, hkv, d = len(lens), 6, 8, 2, 128
+    q = torch.randn(n * qps, hq, d, generator=g).to(dtype)
+    k = torch.randn(sum(lens), hkv, d, generator=g).to(dtype)
+    v = torch.randn(sum(lens), hkv, d, generator=g).to(dtype)
+    cu_k = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    cu_q = torch.arange(0, n + 1, dtype=torch.int32) * qps
+    out, lse = flash_attention_varlen(q.cuda(), k.cuda(), v.cuda(), cu_q.cuda(), cu_k.cuda(), qps, max(lens))
+    ro, rl = O.flash_attention_varlen(q, k, v, cu_q, cu_k, qps, max(lens))
+    assert lse.shape == (n, hq, qps)
+    _assert_close(out, ro, dtype, "out")
+    assert (lse.double().cpu() - rl).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("cfg", [(4, 1, 8, 8, 128, 40), (3, 1, 8, 1, 128, 300), (5, 2, 4, 2, 64, 17), (2, 1, 32, 32, 128, 700), (130, 1, 2, 2, 128, 9)])
+def test_flash_attention_seqlen(dtype, cfg):
+    """The suffix primitive: keys < seq_len[b] only; int32 and int64 lengths; GQA fold; lse [b,q,h];
+    a zero-length row gives out = 0 / lse = -inf; long caches take the 4-warps-per-sequence path."""
+    from hydragen_b200.flash import flash_attention_seqlen
+
+    b, nq, hq, hkv, d, lk = cfg
+    if dtype == torch.float32 and d == 256:
+        pytest.skip("unsupported")
+    g = torch.Generator().manual_seed(lk)
+    q = torch.randn(b, nq, hq, d, generator=g).to(dtype)
+    k = torch.randn(b, lk, hkv, d, generator=g).to(dtype)
+    v = torch.randn(b, lk, hkv, d, generator=g).to(dtype)
+    sl = torch.randint(1, lk + 1, (b,), generator=g)
+    sl[0] = lk
+    if b > 1:
+        sl[1] = 0
+    for sl_dtype in (torch.int32, torch.int64):
+        out, lse = flash_attention_seqlen(q.cuda(), k.cuda(), v.cuda(), sl.to(sl_dtype).cuda())
+        ro, rl = O.flash_attention_seqlen(q, k, v, sl)
+        assert lse.shape == (b, nq, hq)
+        _assert_close(out, ro, dtype, "out")
+        fin = torch.isfinite(rl)
+        assert (lse.double().cpu()[fin] - rl[fin]).abs().max().item() < 5e-3
+        assert torch.equal(torch.isinf(lse.cpu()), ~fin)
+        if b > 1:
+            assert torch.all(out[1] == 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_causal_suffix_prefill(dtype):
+    """flash_attention(causal=True) with sq != sk: bottom-right aligned (hydragen/attention.py:344,
+    hydragen/llama.py:537-542)."""
+    from hydragen_b200.flash import flash_attention
+
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(2, 7, 8, 128, generator=g).to(dtype)
+    k = torch.randn(2, 19, 4, 128, generator=g).to(dtype)
+    v = torch.randn(2, 19, 4, 128, generator=g).to(dtype)
+    out, lse = flash_attention(q.cuda(), k.cuda(), v.cuda(), causal=True)
+    ro, rl = O.flash_attention(q, k, v, causal=True)
+    _assert_close(out, ro, dtype, "out")
+    assert (lse.double().cpu() - rl).abs().max().item() < 5e-3
+
+
+def test_no_unique_keys_early_return():
+    from hydragen_b200.attention import hydragen_attention_nopad
+
+    c = O.build_case([[40], [0, 0, 0, 0]], 8, 8, 128, dtype=torch.bfloat16, seed=9)
+    out = hydragen_attention_nopad(_dev(c["q"]), _dev(c["k"]), _dev(c["v"]), _dev(c["shared_ks"]), _dev(c["shared_vs"]))
+    ref = O.hydragen_attention(**c)
+    _assert_close(out, ref, torch.bfloat16)
+
+
+def test_strided_inputs():
+    """q as a slice of a fused qkv projection, K/V as slices of a larger cache (views, not copies)."""
+    from hydragen_b200.attention import hydragen_attention_nopad
+
+    g = torch.Generator().manual_seed(21)
+    b, hq, hkv, d, ls, lu = 16, 8, 8, 128, 200, 24
+    qkv = torch.randn(b, 1, 3 * hq * d, generator=g).to(torch.bfloat16).cuda()
+    q = qkv[..., : hq * d].view(b, 1, hq, d)
+    cache = torch.randn(b + 3, lu + 8, hkv, d, generator=g).to(torch.bfloat16).cuda()
+    cache_v = torch.randn(b + 3, lu + 8, hkv, d, generator=g).to(torch.bfloat16).cuda()
+    k, v = cache[:b], cache_v[:b]
+    flat = torch.randn(2 * ls + 50, hkv, d, generator=g).to(torch.bfloat16).cuda()
+    flat_v = torch.randn(2 * ls + 50, hkv, d, generator=g).to(torch.bfloat16).cuda()
+    sk, sv = flat[: 2 * ls].view(2, ls, hkv, d), flat_v[: 2 * ls].view(2, ls, hkv, d)
+    sl = torch.randint(1, lu + 1, (b,), generator=g).cuda()
+    out = hydragen_attention_nopad(q, k, v, [sk], [sv], seq_len=sl)
+    ref = O.hydragen_attention_nopad(q.cpu(), k.cpu(), v.cpu(), [sk.cpu()], [sv.cpu()], seq_len=sl.cpu())
+    _assert_close(out, ref, torch.bfloat16)
+
+
+def test_cuda_graph_capture_and_replay():
+    """The operator is capturable (no sync / host reads on the launch path) and replays correctly after
+    the inputs change in place -- the way hydragen/llama.py:781-866 uses it."""
+    from hydragen_b200.attention import hydragen_attention_nopad
+
+    g = torch.Generator().manual_seed(2)
+    b, h, d, ls, lu = 64, 8, 128, 384, 16
+    mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16).cuda()
+    q, k, v, sk, sv = mk(b, 1, h, d), mk(b, lu, h, d), mk(b, lu, h, d), mk(1, ls, h, d), mk(1, ls, h, d)
+    sl = torch.full((b,), 3, dtype=torch.int64).cuda()
+    hydragen_attention_nopad(q, k, v, [sk], [sv], seq_len=sl)  # warm-up (lazy init outside capture)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            hydragen_attention_nopad(q, k, v, [sk], [sv], seq_len=sl)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = hydragen_attention_nopad(q, k, v, [sk], [sv], seq_len=sl)
+    for step in range(3):
+        q.copy_(mk(b, 1, h, d))
+        sl.fill_(5 + 4 * step)
+        graph.replay()
+        torch.cuda.synchronize()
+        ref = O.hydragen_attention_nopad(q.cpu(), k.cpu(), v.cpu(), [sk.cpu()], [sv.cpu()], seq_len=sl.cpu())
+        _assert_close(out, ref, torch.bfloat16, f"replay {step}")
+
+
+def test_full_size_microbenchmark_config_properties():
+    """BASELINE.json configs[1] at full size (B=1024, prefix 2048, 32 heads, d=128, bf16), beyond what
+    the CPU oracle finishes quickly.  Size-independent checks:
+      1. the tcgen05 prefix kernel and the CUDA-core row-wise kernel (independent code) agree on
+         out and lse for every (sequence, head);
+      2. decomposed attention == attention over the explicit concatenation [prefix ; suffix]
+         computed by the row-wise kernel in one pass (the reference test's criterion,
+         tests/test_attention.py:132-187), on a batch subset that fits memory;
+      3. a CPU-oracle spot check of 4 sequences."""
+    from hydragen_b200.attention import hydragen_attention_nopad
+    from hydragen_b200.flash import flash_attention_seqlen, prefix_attention_grouped
+
+    torch.manual_seed(0)
+    B, Ls, Lu, H, D = 1024, 2048, 32, 32, 128
+    dev = "cuda:0"
+    q = torch.randn(B, 1, H, D, device=dev, dtype=torch.bfloat16)
+    k = torch.randn(B, Lu, H, D, device=dev, dtype=torch.bfloat16)
+    v = torch.randn(B, Lu, H, D, device=dev, dtype=torch.bfloat16)
+    sk = torch.randn(1, Ls, H, D, device=dev, dtype=torch.bfloat16)
+    sv = torch.randn(1, Ls, H, D, device=dev, dtype=torch.bfloat16)
+    sl = torch.randint(1, Lu + 1, (B,), device=dev)
+
+    os.environ["HYDRAGEN_B200_PREFIX_BACKEND"] = "tcgen05"
+    o_tc, l_tc = prefix_attention_grouped(q, sk, sv, n_groups=1)
+    os.environ["HYDRAGEN_B200_PREFIX_BACKEND"] = "rowwise"
+    o_rw, l_rw = prefix_attention_grouped(q, sk, sv, n_groups=1)
+    os.environ["HYDRAGEN_B200_PREFIX_BACKEND"] = "auto"
+    torch.cuda.synchronize()
+    assert (l_tc - l_rw).abs().max().item() < 5e-3
+    assert (o_tc.float() - o_rw.float()).abs().max().item() < 4e-3  # |out| <~ 0.1 here; 1 bf16 ulp
+
+    out = hydragen_attention_nopad(q, k, v, [sk], [sv], seq_len=sl)
+    nb = 128
+    kc = torch.cat([sk.expand(nb, -1, -1, -1), k[:nb]], dim=1)
+    vc = torch.cat([sv.expand(nb, -1, -1, -1), v[:nb]], dim=1)
+    o_cat, _ = flash_attention_seqlen(q[:nb], kc, vc, seq_len=sl[:nb] + Ls)
+    torch.cuda.synchronize()
+    _assert_close(out[:nb], o_cat, torch.bfloat16, "decomposed vs concatenated")
+
+    idx = [0, 1, 511, 1023]
+    ref = O.hydragen_attention_nopad(q[idx].cpu(), k[idx].cpu(), v[idx].cpu(), [sk.cpu()], [sv.cpu()], seq_len=sl[idx].cpu(), compute_dtype=torch.float32)
+    _assert_close(out[idx], ref, torch.bfloat16, "oracle spot check")
+
+
+def test_kv_append():
+    from hydragen_b200 import _lib
+
+    g = torch.Generator().manual_seed(4)
+    b, nq, hkv, d, lk = 37, 1, 8, 128, 48
+    kc = torch.zeros(b + 2, lk, hkv, d, dtype=torch.bfloat16).cuda()
+    vc = torch.zeros_like(kc)
+    kn = torch.randn(b, nq, hkv, d, generator=g).to(torch.bfloat16).cuda()
+    vn = torch.randn(b, nq, hkv, d, generator=g).to(torch.bfloat16).cuda()
+    pos = torch.randint(0, lk, (b, nq), generator=g).cuda()
+    _lib.kv_append(kn, vn, pos, kc, vc)
+    # the reference's formulation: scatter_ with a fully expanded index (hydragen/llama.py:250-257)
+    rk = torch.zeros_like(kc)
+    rv = torch.zeros_like(vc)
+    idx = pos.view(b, nq, 1, 1).expand(b, nq, hkv, d)
+    rk[:b].scatter_(1, idx, kn)
+    rv[:b].scatter_(1, idx, vn)
+    assert torch.equal(kc, rk) and torch.equal(vc, rv)
