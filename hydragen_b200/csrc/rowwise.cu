@@ -284,6 +284,194 @@ __global__ void __launch_bounds__(kRowwiseWarps * 32) rowwise_attn_kernel(const 
   }
 }
 
+// ---- decode fast path: one LPK-lane slot per (sequence, kv head) ------------------------------
+// The shape that every decode step of the reference produces (hydragen/llama.py:564-587): nq == 1,
+// each (sequence, kv head) unit owns `len_b` keys.  A slot of LPK = D/VEC lanes (16 for d = 128,
+// 16-bit) owns one unit and walks its keys in order, U keys (2U independent 128-bit loads per lane)
+// per trip; the R = Hq/Hkv query rows of the unit share every K/V row.  Adjacent slots are adjacent
+// kv heads of the same cache row, so a warp load covers whole contiguous 256-byte head rows.  No
+// shared memory, no cross-slot merge, 16 units per 256-thread CTA; register use is small enough for
+// >= 24 resident warps per SM, which is what keeps enough bytes in flight for HBM (Little's law:
+// ~31 KB per SM at 6.5 TB/s x 700 ns).  The loop trip count is made warp-uniform (max over the
+// warp's slots) so the LPK-lane shuffles never diverge; out-of-range keys are predicated off and
+// never read (xformers_stuff.py:274-279).
+template <typename T, int D, int R, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwiseParams p) {
+  constexpr int VEC = Vec16<T>::VEC;
+  constexpr int LPK = D / VEC;
+  static_assert(LPK >= 1 && LPK <= 32 && (LPK & (LPK - 1)) == 0, "head_dim not supported for this dtype");
+  constexpr int SLOTS = 256 / LPK;
+  const int tid = threadIdx.x;
+  const int dl = tid % LPK;
+  const int64_t unit = (int64_t)blockIdx.x * SLOTS + tid / LPK;
+  const int64_t n_units = (int64_t)p.b * p.hkv;
+  const bool valid = unit < n_units;
+  const int b_idx = valid ? (int)(unit / p.hkv) : 0;
+  const int kvh = valid ? (int)(unit % p.hkv) : 0;
+
+  int len = 0;
+  if (valid) {
+    len = p.lk;
+    if (p.seq_lens != nullptr) {
+      const int64_t sl = p.seq_lens_i64 ? __ldg(reinterpret_cast<const int64_t*>(p.seq_lens) + b_idx)
+                                        : (int64_t)__ldg(reinterpret_cast<const int32_t*>(p.seq_lens) + b_idx);
+      len = (int)max((int64_t)0, min((int64_t)len, sl));
+    }
+  }
+  // first output row of the unit: rows (b, 0, kvh*R + r), r < R, are contiguous
+  const int64_t orow0 = (int64_t)b_idx * p.hq + (int64_t)kvh * R;
+  const int np = p.partials.n;
+
+  // independent of len: the query rows and the first prefix partial (the common decode case is one
+  // shared level) are requested before the key loop so their latency overlaps it
+  uint4 qraw[R], p0raw[R];
+  float p0lse[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    qraw[r] = make_uint4(0, 0, 0, 0);
+    p0raw[r] = make_uint4(0, 0, 0, 0);
+    p0lse[r] = -INFINITY;
+    if (valid) {
+      qraw[r] = ld_v4(reinterpret_cast<const T*>(p.q) + (int64_t)b_idx * p.q_stride_b + (int64_t)(kvh * R + r) * p.q_stride_h + dl * VEC);
+      if (np > 0) {
+        p0raw[r] = ld_stream_v4(reinterpret_cast<const T*>(p.partials.outs[0]) + (orow0 + r) * D + dl * VEC);
+        p0lse[r] = __ldg(p.partials.lses[0] + orow0 + r);
+      }
+    }
+  }
+  int len_max = len;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) len_max = max(len_max, __shfl_xor_sync(0xffffffffu, len_max, o));
+
+  const T* kb = reinterpret_cast<const T*>(p.k) + (int64_t)b_idx * p.kv_stride_b + (int64_t)kvh * p.kv_stride_h + dl * VEC;
+  const T* vb = reinterpret_cast<const T*>(p.v) + (int64_t)b_idx * p.kv_stride_b + (int64_t)kvh * p.kv_stride_h + dl * VEC;
+
+  float qf[R][VEC];
+  RowState<VEC> st[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    Vec16<T>::unpack(qraw[r], qf[r]);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) qf[r][e] *= p.scale_log2;  // scores come out in the log2 domain
+    st[r].m = -INFINITY;
+    st[r].l = 0.f;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) st[r].acc[e] = 0.f;
+  }
+
+  for (int j0 = 0; j0 < len_max; j0 += U) {
+    uint4 kraw[U], vraw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) kraw[u] = (j0 + u < len) ? ld_stream_v4(kb + (int64_t)(j0 + u) * p.kv_stride_s) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) vraw[u] = (j0 + u < len) ? ld_stream_v4(vb + (int64_t)(j0 + u) * p.kv_stride_s) : make_uint4(0, 0, 0, 0);
+    float s[U][R];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float kf[VEC];
+      Vec16<T>::unpack(kraw[u], kf);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) d = fmaf(qf[r][e], kf[e], d);
+#pragma unroll
+        for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        s[u][r] = (j0 + u < len) ? d : -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float m_new = st[r].m;
+#pragma unroll
+      for (int u = 0; u < U; ++u) m_new = fmaxf(m_new, s[u][r]);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = fast_exp2(st[r].m - m_safe);
+      float pu[U];
+      float psum = 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        pu[u] = fast_exp2(s[u][r] - m_safe);
+        psum += pu[u];
+      }
+      st[r].l = st[r].l * alpha + psum;
+      st[r].m = m_new;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) st[r].acc[e] *= alpha;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float vf[VEC];
+        Vec16<T>::unpack(vraw[u], vf);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) st[r].acc[e] = fmaf(pu[u], vf[e], st[r].acc[e]);
+      }
+    }
+  }
+
+  if (!valid) return;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int64_t orow = orow0 + r;
+    const float l = st[r].l;
+    float lse = (l > 0.f) ? (st[r].m + fast_log2(l)) * kLn2 : -INFINITY;
+    const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+    float o[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) o[e] = st[r].acc[e] * inv_l;
+    if (np > 0) {
+      float pl[HG_MAX_COMBINE];
+      uint4 praw[HG_MAX_COMBINE];
+      pl[0] = p0lse[r];
+      praw[0] = p0raw[r];
+      float mx = fmaxf(lse, pl[0]);
+#pragma unroll
+      for (int i = 1; i < HG_MAX_COMBINE; ++i) {
+        if (i < np) {
+          pl[i] = __ldg(p.partials.lses[i] + orow);
+          praw[i] = ld_stream_v4(reinterpret_cast<const T*>(p.partials.outs[i]) + orow * D + dl * VEC);
+          mx = fmaxf(mx, pl[i]);
+        }
+      }
+      const float mx_safe = (mx == -INFINITY) ? 0.f : mx;
+      const float w_s = __expf(lse - mx_safe);
+      float den = w_s;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) o[e] *= w_s;
+#pragma unroll
+      for (int i = 0; i < HG_MAX_COMBINE; ++i) {
+        if (i < np) {
+          const float w = __expf(pl[i] - mx_safe);
+          den += w;
+          float f[VEC];
+          Vec16<T>::unpack(praw[i], f);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) o[e] = fmaf(w, f[e], o[e]);
+        }
+      }
+      const float inv = den > 0.f ? 1.f / den : 0.f;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) o[e] *= inv;
+      lse = den > 0.f ? mx_safe + __logf(den) : -INFINITY;
+    }
+    st_v4(reinterpret_cast<T*>(p.out) + orow * D + dl * VEC, Vec16<T>::pack(o));
+    if (p.lse != nullptr && dl == 0) p.lse[orow] = lse;
+  }
+}
+
+template <typename T, int D, int R>
+static int launch_decode_slot(const RowwiseParams& p, cudaStream_t s) {
+  constexpr int VEC = Vec16<T>::VEC;
+  constexpr int SLOTS = 256 / (D / VEC);
+  const int64_t n_units = (int64_t)p.b * p.hkv;
+  const int64_t blocks = (n_units + SLOTS - 1) / SLOTS;
+  if (blocks > 0x7fffffffLL) return set_error(HG_ERR_UNSUPPORTED, "rowwise: too many units (%lld)", (long long)n_units);
+  if (p.lk <= 8)  // a handful of keys: fewer registers -> more resident warps to hide the dependent-load chain
+    decode_slot_kernel<T, D, R, 2, (R == 1 ? 4 : (R <= 4 ? 2 : 1))><<<(unsigned)blocks, 256, 0, s>>>(p);
+  else
+    decode_slot_kernel<T, D, R, 4, (R == 1 ? 3 : (R <= 4 ? 2 : 1))><<<(unsigned)blocks, 256, 0, s>>>(p);
+  return check_launch("decode_slot_attn");
+}
+
 template <typename T, int D, int WPI, int R>
 static int launch_rowwise_inst(const RowwiseParams& p, cudaStream_t s) {
   constexpr int ITEMS = kRowwiseWarps / WPI;
@@ -297,6 +485,17 @@ static int launch_rowwise_inst(const RowwiseParams& p, cudaStream_t s) {
 template <typename T, int D>
 static int launch_rowwise_d(const RowwiseParams& p, cudaStream_t s) {
   const int M = p.nq * (p.hq / p.hkv);
+  // decode shape with enough independent units (or few keys): the slot kernel
+  const int64_t n_units = (int64_t)p.b * p.hkv;
+  if (p.nq == 1 && p.cu_seqlens_k == nullptr && p.kv_group_size == 1 && (n_units >= 2048 || p.lk <= 64)) {
+    switch (M) {
+      case 1: return launch_decode_slot<T, D, 1>(p, s);
+      case 2: return launch_decode_slot<T, D, 2>(p, s);
+      case 4: return launch_decode_slot<T, D, 4>(p, s);
+      case 8: return launch_decode_slot<T, D, 8>(p, s);
+      default: break;
+    }
+  }
   // long per-sequence KV: split the keys of one unit over the 4 warps of the CTA
   const bool wide = p.lk > 256;
   if (M == 1) return wide ? launch_rowwise_inst<T, D, 4, 1>(p, s) : launch_rowwise_inst<T, D, 1, 1>(p, s);
