@@ -303,31 +303,47 @@ def run_ours(a):
     tf_peak = float(peaks.get("bf16_tflops", 1590.0))
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json, burst)" if peaks else "fallback (B200_PROFILING.md)"
-    n_ev = 4
-    pre_ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(L)] for _ in range(n_ev)]
-    suf_ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(L)] for _ in range(n_ev)]
     from hydragen_b200.flash import suffix_attention_fused
 
-    for it in range(n_ev):
+    # Per-kernel time, live: a CUDA graph holding ONLY that kernel's launches of one step (one per layer, each
+    # on its own layer's tensors so nothing is L2-warm from a previous launch), replayed and timed with CUDA
+    # events on the launching stream.  (Events around eager launches would time the Python launch gaps.)
+    pre_out = [None] * L
+
+    def only_prefix():
         for i in range(L):
-            _lib.kv_append(kn[i], vn[i], pos, uniq[i, 0], uniq[i, 1])
-            pre_ev[it][i][0].record()
-            so, sl_ = prefix_attention_grouped(qs[i], shared_k[i], shared_v[i], n_groups=1)
-            pre_ev[it][i][1].record()
-            suf_ev[it][i][0].record()
-            suffix_attention_fused(qs[i], uniq[i, 0], uniq[i, 1], seq_lens, causal=False, partial_outs=[so], partial_lses=[sl_])
-            suf_ev[it][i][1].record()
-    torch.cuda.synchronize()
-    pre_us = sorted(p[0].elapsed_time(p[1]) * 1e3 for it in pre_ev[1:] for p in it)
-    suf_us = sorted(p[0].elapsed_time(p[1]) * 1e3 for it in suf_ev[1:] for p in it)
-    pre_t, suf_t = sum(pre_us) / len(pre_us), sum(suf_us) / len(suf_us)
+            pre_out[i] = prefix_attention_grouped(qs[i], shared_k[i], shared_v[i], n_groups=1)
+
+    def only_suffix():
+        for i in range(L):
+            suffix_attention_fused(qs[i], uniq[i, 0], uniq[i, 1], seq_lens, causal=False, partial_outs=[pre_out[i][0]], partial_lses=[pre_out[i][1]])
+
+    def time_kernel_graph(fn, reps=20):
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(reps):
+            g.replay()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) * 1e3 / (reps * L)  # us per launch
+
+    pre_t = time_kernel_graph(only_prefix)
+    suf_t = time_kernel_graph(only_suffix)
     pre_flops = 4.0 * B * H * a.prefix_len * D
     esz = 2
     suf_bytes = 2.0 * B * a.suffix_len * HKV * D * esz + 3.0 * B * H * D * esz + 2.0 * B * H * 4  # K,V + q,partial,out + 2 lse
     roofline = {"kernel": "prefix_attn_sm100_kernel (tcgen05)", "bound": "tensor", "achieved": pre_flops / pre_t / 1e6, "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": pre_flops / pre_t / 1e6 / tf_peak, "traffic": None, "us_per_launch": pre_t,
                 "algorithmic_flop_per_launch": pre_flops, "peak_source": peak_src}
-    roofline_suffix = {"kernel": "rowwise_attn_kernel (suffix + combine)", "bound": "hbm", "achieved": suf_bytes / suf_t / 1e3, "peak": hbm_peak,
+    roofline_suffix = {"kernel": "decode_slot_kernel (suffix + combine)", "bound": "hbm", "achieved": suf_bytes / suf_t / 1e3, "peak": hbm_peak,
                        "unit": "GB/s", "frac": suf_bytes / suf_t / 1e3 / hbm_peak, "traffic": None, "us_per_launch": suf_t,
                        "algorithmic_bytes_per_launch": suf_bytes, "peak_source": peak_src}
     prof = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch read from the committed ncu --set full capture

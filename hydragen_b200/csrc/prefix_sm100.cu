@@ -6,30 +6,32 @@
 //
 // Inter-sequence batching makes this a dense problem: for one (group, head) the queries of every
 // sequence sharing the prefix form Q[q_per_group x d] and are multiplied against the single
-// K,V[k_len x d] of that prefix.  One CTA owns a 128-row Q tile of one head and streams the
-// prefix in 128-key blocks:
+// K,V[k_len x d] of that prefix.  One CTA owns TWO 128-row Q tiles (A, B) of one head and streams
+// the prefix in 128-key blocks; the two tiles ping-pong so that the tensor pipe works on one tile
+// while the softmax warps work on the other, and every K/V block fetched feeds 256 query rows:
 //
-//   warp 0 (1 lane)  TMA producer: Q once, then K_j / V_j into 2-deep smem rings
+//   warp 0 (1 lane)  TMA producer: Q_A, Q_B once, then K_j / V_j into 2-deep smem rings
 //                    (cp.async.bulk.tensor, SWIZZLE_128B boxes of 128 rows x 64 elements)
-//   warp 1 (1 lane)  MMA issuer:   S_j = Q K_j^T  (SS form, both operands K-major in smem,
-//                                  128x128x16 per instruction, fp32 accumulate in TMEM)
-//                                  O += P_j V_j   (TS form: P_j read from TMEM as the A operand,
-//                                  V_j straight from its row-major smem tile as an MN-major B
-//                                  operand -- no transpose pass)
-//   warp 2           TMEM allocator (512 columns: S0 | S1 | O)
-//   warps 4-7        softmax: thread t owns row t (tcgen05.ld 32x32b: lane == row, so the row
-//                    max / row sum need no shuffles), exp2 with the scale folded into one FFMA,
-//                    P_j written back over S_j in TMEM as packed 16-bit, lazy rescale of O
-//                    (only when the running max grows by more than 2^8), epilogue O / l -> gmem,
+//   warp 1 (1 lane)  MMA issuer, per key block j:  PV_A(j)  QK_A(j+1)  PV_B(j)  QK_B(j+1)
+//                      S_t = Q_t K_j^T  (SS form, both operands K-major in smem, 128x128x16 per
+//                                        instruction, fp32 accumulate in TMEM)
+//                      O_t += P_t V_j   (TS form: P_t read from TMEM as the A operand, V_j straight
+//                                        from its row-major smem tile as an MN-major B operand --
+//                                        no transpose pass)
+//   warp 2           TMEM allocator (512 columns: S_A | S_B | O_A | O_B)
+//   warps 4-7        softmax of tile A, warps 8-11 softmax of tile B: thread t owns row t
+//                    (tcgen05.ld 32x32b: lane == row, so the row max / row sum need no shuffles),
+//                    exp2 with the scale folded into one FFMA, P_t written back over S_t in TMEM as
+//                    packed 16-bit, lazy rescale of O_t (only when the running max grows by more
+//                    than 2^8), epilogue O_t / l -> swizzled smem (the dead Q_t tile) -> TMA store,
 //                    LSE written directly in [b, nq, hq].
 //
-// S is double buffered so that Q K_{j+1}^T runs on the tensor pipe while the softmax warps work
-// on S_j.  All producer/consumer edges are mbarriers (TMA complete_tx, tcgen05.commit, thread
-// arrives); there is no __syncthreads in the main loop.
+// All producer/consumer edges are mbarriers (TMA complete_tx, tcgen05.commit, thread arrives); there
+// is no __syncthreads in the main loop.  tcgen05.commit covers every MMA issued before it, so the
+// arrival of S_t(j) also tells the softmax warps that PV_t(j-1) has retired (O_t is stable).
 //
-// Algorithmic work per CTA tile: 4 * 128 * k_len * d FLOP.  Bound: tensor pipe (AI ~ 680 FLOP/B
-// at the 7B config), with the MUFU exp2 rate (16/clk/SM == the 128x128x128 MMA rate) the
-// co-limiter.
+// Algorithmic work per CTA: 4 * rows * k_len * d FLOP.  Bound: tensor pipe (AI ~ 680 FLOP/B at the
+// 7B config), with the MUFU exp2 rate (16/clk/SM == the 128x128x128 MMA rate) the co-limiter.
 #include <cuda.h>
 
 #include <type_traits>
@@ -42,9 +44,11 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 128;
-constexpr int kThreads = 256;
+constexpr int kTiles = 2;  // Q tiles per CTA (ping-pong)
+constexpr int kThreads = 384;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmemS0 = 0, kTmemS1 = 128, kTmemO = 256;
+__host__ __device__ constexpr uint32_t tmem_s(int t) { return (uint32_t)t * 128u; }        // S_t (P_t aliases its first 64 columns)
+__host__ __device__ constexpr uint32_t tmem_o(int t) { return 256u + (uint32_t)t * 128u; }  // O_t
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -72,6 +76,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// One lane of the (converged) warp, known to the compiler as such: the uniform datapath can then
+// feed TMA / UMMA descriptors without a per-lane waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -90,39 +107,44 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem]
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]; descriptors passed as (lo, hi) halves so that stepping the start
+// address along K is one 32-bit add per operand
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
       "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      ".reg .b64 db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
       "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
 // Shared-memory matrix descriptor (sm_100 UMMA): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
-// version=1 [46,48) | layout [61,64) with SWIZZLE_128B = 2.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+// version=1 [46,48) | layout [61,64) with SWIZZLE_128B = 2.  lo = start | LBO, hi = SBO | version | layout.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
 }
 
 // Instruction descriptor, kind::f16: D fmt [4,6) (1 = f32) | A fmt [7,10) | B fmt [10,13) (0 = f16, 1 = bf16) |
@@ -179,23 +201,46 @@ __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
   return r;
 }
 
+#define HG_W16(a, o)                                                                                                     \
+  "r"(a[o + 0]), "r"(a[o + 1]), "r"(a[o + 2]), "r"(a[o + 3]), "r"(a[o + 4]), "r"(a[o + 5]), "r"(a[o + 6]), "r"(a[o + 7]), \
+      "r"(a[o + 8]), "r"(a[o + 9]), "r"(a[o + 10]), "r"(a[o + 11]), "r"(a[o + 12]), "r"(a[o + 13]), "r"(a[o + 14]),       \
+      "r"(a[o + 15])
+#define HG_TMEM_ST16(taddr, a, o)                                                                          \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::HG_W16(a, o), \
+               "r"(taddr)                                                                                  \
+               : "memory")
+
+// smem tile (generic-proxy writes fenced by the caller) -> global through the tensor map
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_and_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+template <int ID, int THREADS>
+__device__ __forceinline__ void named_bar_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(THREADS) : "memory");
+}
+
 template <int D>
 struct SmemLayout {
   static constexpr int kHalves = D / 64;                 // 64-element (128-byte) swizzle atoms along d
   static constexpr int kTileBytes = BLOCK_N * D * 2;     // one Q / K / V tile
   static constexpr int kHalfBytes = BLOCK_N * 64 * 2;    // one TMA box: 128 rows x 128 B
-  static constexpr int kQ = 0;
-  static constexpr int kK = kTileBytes;                  // 2 stages
-  static constexpr int kV = kTileBytes * 3;              // 2 stages
-  static constexpr int kBars = kTileBytes * 5;
+  static constexpr int kQ = 0;                           // 2 tiles (A, B); reused as the output staging tiles
+  static constexpr int kK = kTileBytes * 2;              // 2 stages
+  static constexpr int kV = kTileBytes * 4;              // 2 stages
+  static constexpr int kBars = kTileBytes * 6;
   static constexpr int kTotal = kBars + 256;
 };
 
 struct Barriers {
-  uint64_t q_full;
+  uint64_t q_full[kTiles];
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
-  uint64_t s_full[2], p_full[2];
-  uint64_t pv_done;
+  uint64_t s_full[kTiles], p_full[kTiles], o_full[kTiles];
   uint32_t tmem_base;
 };
 
@@ -204,9 +249,9 @@ struct Barriers {
 template <typename T, int D>
 __global__ void __launch_bounds__(kThreads, 1)
     prefix_attn_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                             const __grid_constant__ CUtensorMap tmap_v, T* __restrict__ out, float* __restrict__ lse,
-                             const int32_t* __restrict__ cu_seqlens_k, int q_per_group, int tiles_per_group, int k_len_uniform,
-                             int hq, int hkv, float scale_log2) {
+                             const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                             T* __restrict__ out, float* __restrict__ lse, const int32_t* __restrict__ cu_seqlens_k,
+                             int q_per_group, int tiles_per_group, int k_len_uniform, int hq, int hkv, float scale_log2) {
   using L = SmemLayout<D>;
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t kIdescQK = make_idesc(kFmt, 0, BLOCK_M, BLOCK_N);
@@ -220,8 +265,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int tile = blockIdx.x, head = blockIdx.y;
   const int grp = tile / tiles_per_group, mt = tile % tiles_per_group;
   const int kvh = head / (hq / hkv);
-  const int q_row0 = grp * q_per_group + mt * BLOCK_M;
-  const int rows_valid = min(BLOCK_M, q_per_group - mt * BLOCK_M);
+  const int q_row0 = grp * q_per_group + mt * (kTiles * BLOCK_M);
+  const int rows_left = q_per_group - mt * (kTiles * BLOCK_M);  // > 0
+  const bool two = rows_left > BLOCK_M;                         // tile B holds valid rows
   int k_start, k_len;
   if (cu_seqlens_k != nullptr) {
     k_start = __ldg(cu_seqlens_k + grp);
@@ -233,12 +279,13 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int n_blocks = (k_len + BLOCK_N - 1) / BLOCK_N;
 
   if (n_blocks == 0) {  // empty prefix: out = 0, lse = -inf (uniform branch for the whole CTA)
-    for (int idx = threadIdx.x; idx < rows_valid * (D / 8); idx += kThreads) {
+    const int rows = min(kTiles * BLOCK_M, rows_left);
+    for (int idx = threadIdx.x; idx < rows * (D / 8); idx += kThreads) {
       const int r = idx / (D / 8), c = idx % (D / 8);
       st_v4(out + ((int64_t)(q_row0 + r) * hq + head) * D + c * 8, make_uint4(0, 0, 0, 0));
     }
     if (lse != nullptr)
-      for (int r = threadIdx.x; r < rows_valid; r += kThreads) lse[(int64_t)(q_row0 + r) * hq + head] = -INFINITY;
+      for (int r = threadIdx.x; r < rows; r += kThreads) lse[(int64_t)(q_row0 + r) * hq + head] = -INFINITY;
     return;
   }
 
@@ -247,18 +294,19 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_v) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(&bars->q_full, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->q_full[i], 1);
       mbar_init(&bars->k_full[i], 1);
       mbar_init(&bars->k_empty[i], 1);
       mbar_init(&bars->v_full[i], 1);
       mbar_init(&bars->v_empty[i], 1);
       mbar_init(&bars->s_full[i], 1);
-      mbar_init(&bars->p_full[i], 128);
+      mbar_init(&bars->p_full[i], BLOCK_M);
+      mbar_init(&bars->o_full[i], 1);
     }
-    mbar_init(&bars->pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -272,13 +320,21 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_base);
 
+  // Register budget (setmaxnreg must sit inside the role branch it applies to): the producer
+  // warpgroup gives registers back, the two softmax warpgroups (128 live fp32 scores per thread)
+  // take them: 128 x 88 + 256 x 208 <= 64K.
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 0) {
     // =============================== TMA producer ===========================================
-    if (lane == 0) {
-      mbar_expect_tx(&bars->q_full, L::kTileBytes);
+    if (elect_one()) {
+      for (int t = 0; t < (two ? 2 : 1); ++t) {
+        mbar_expect_tx(&bars->q_full[t], L::kTileBytes);
 #pragma unroll
-      for (int h = 0; h < L::kHalves; ++h)
-        tma_load_2d(smem + L::kQ + h * L::kHalfBytes, &tmap_q, head * D + h * 64, q_row0, &bars->q_full);
+        for (int h = 0; h < L::kHalves; ++h)
+          tma_load_2d(smem + L::kQ + t * L::kTileBytes + h * L::kHalfBytes, &tmap_q, head * D + h * 64, q_row0 + t * BLOCK_M,
+                      &bars->q_full[t]);
+      }
       for (int j = 0; j < n_blocks; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
@@ -297,154 +353,222 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =============================================
-    if (lane == 0) {
-      const uint32_t q_addr = smem_u32(smem + L::kQ);
-      // S = Q K^T: D/16 instructions of 128x128x16; operand k-slice kk lives in swizzle atom kk/4
-      // at byte offset (kk%4)*32 inside the 128-byte row.
-      auto issue_qk = [&](int st, uint32_t s_col) {
-        const uint32_t k_addr = smem_u32(smem + L::kK + st * L::kTileBytes);
+    if (elect_one()) {
+      // S_t = Q_t K^T: D/16 instructions of 128x128x16; operand k-slice kk lives in swizzle atom kk/4
+      // at byte offset (kk%4)*32 inside the 128-byte row (start-address field is in 16-byte units).
+      constexpr uint32_t kHiK = desc_hi(1024);  // K-major SWIZZLE_128B: 8-row groups 1024 B apart
+      const uint32_t q_lo0 = desc_lo(smem_u32(smem + L::kQ), 0);
+      const uint32_t k_lo0 = desc_lo(smem_u32(smem + L::kK), 0);
+      const uint32_t v_lo0 = desc_lo(smem_u32(smem + L::kV), L::kHalfBytes);
+      auto issue_qk = [&](int t, int st) {
+        const uint32_t q_lo = q_lo0 + t * (L::kTileBytes >> 4);
+        const uint32_t k_lo = k_lo0 + st * (L::kTileBytes >> 4);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk / 4) * L::kHalfBytes + (kk % 4) * 32;
-          umma_ss(tmem + s_col, make_smem_desc(q_addr + off, 0, 1024), make_smem_desc(k_addr + off, 0, 1024), kIdescQK,
-                  kk > 0 ? 1u : 0u);
+          const uint32_t off = ((kk / 4) * L::kHalfBytes + (kk % 4) * 32) >> 4;
+          umma_ss(tmem + tmem_s(t), q_lo + off, kHiK, k_lo + off, kHiK, kIdescQK, kk > 0 ? 1u : 0u);
         }
       };
-      // O (+)= P V: BLOCK_N/16 instructions of 128xDx16; A = P (16-bit, 8 TMEM columns per k-slice),
-      // B = V tile rows [kk*16, kk*16+16) as an MN-major operand: 8-row groups 1024 B apart (SBO),
-      // 64-element column halves one TMA box apart (LBO).
-      auto issue_pv = [&](int st, uint32_t p_col, bool first) {
-        const uint32_t v_addr = smem_u32(smem + L::kV + st * L::kTileBytes);
+      // O_t (+)= P_t V: BLOCK_N/16 instructions of 128xDx16; A = P_t (16-bit, 8 TMEM columns per
+      // k-slice), B = V tile rows [kk*16, kk*16+16) as an MN-major operand: 8-row groups 1024 B apart
+      // (SBO), 64-element column halves one TMA box apart (LBO).
+      auto issue_pv = [&](int t, int st, bool first) {
+        const uint32_t v_lo = v_lo0 + st * (L::kTileBytes >> 4);
 #pragma unroll
         for (int kk = 0; kk < BLOCK_N / 16; ++kk) {
-          umma_ts(tmem + kTmemO, tmem + p_col + kk * 8, make_smem_desc(v_addr + kk * 2048, L::kHalfBytes, 1024), kIdescPV,
-                  (first && kk == 0) ? 0u : 1u);
+          umma_ts(tmem + tmem_o(t), tmem + tmem_s(t) + kk * 8, v_lo + kk * (2048 >> 4), kHiK, kIdescPV, (first && kk == 0) ? 0u : 1u);
         }
       };
 
-      mbar_wait(&bars->q_full, 0);
+      mbar_wait(&bars->q_full[0], 0);
       mbar_wait(&bars->k_full[0], 0);
       tc_fence_after();
-      issue_qk(0, kTmemS0);
-      umma_commit(&bars->k_empty[0]);
+      issue_qk(0, 0);
       umma_commit(&bars->s_full[0]);
+      if (two) {
+        mbar_wait(&bars->q_full[1], 0);
+        tc_fence_after();
+        issue_qk(1, 0);
+        umma_commit(&bars->s_full[1]);
+      }
+      umma_commit(&bars->k_empty[0]);
       for (int j = 0; j < n_blocks; ++j) {
-        if (j + 1 < n_blocks) {
-          const int st = (j + 1) & 1;
-          mbar_wait(&bars->k_full[st], ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_qk(st, st ? kTmemS1 : kTmemS0);
-          umma_commit(&bars->k_empty[st]);
-          umma_commit(&bars->s_full[st]);
-        }
-        const int st = j & 1;
+        const int st = j & 1, nst = st ^ 1;
         const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&bars->p_full[st], ph);
+        const bool has_next = j + 1 < n_blocks;
+        // ---- tile A: PV_A(j), then QK_A(j+1) while softmax B(j) is still running
+        mbar_wait(&bars->p_full[0], j & 1);
         mbar_wait(&bars->v_full[st], ph);
         tc_fence_after();
-        issue_pv(st, st ? kTmemS1 : kTmemS0, j == 0);
-        umma_commit(&bars->v_empty[st]);
-        umma_commit(&bars->pv_done);
-      }
-    }
-  } else if (warp >= 4) {
-    // =============================== softmax / correction / epilogue ==========================
-    const int wq = warp - 4;           // == warp % 4: the TMEM lane quarter this warp may access
-    const int row = wq * 32 + lane;    // row of the tile == TMEM lane
-    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    float m_used = -INFINITY;          // raw-score max the exponentials are referenced to
-    float l = 0.f;
-
-    for (int j = 0; j < n_blocks; ++j) {
-      const int buf = j & 1;
-      const uint32_t s_addr = tmem + lane_base + (buf ? kTmemS1 : kTmemS0);
-      mbar_wait(&bars->s_full[buf], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t sr[128];
-      HG_TMEM_LD32(s_addr + 0, sr, 0);
-      HG_TMEM_LD32(s_addr + 32, sr, 32);
-      HG_TMEM_LD32(s_addr + 64, sr, 64);
-      HG_TMEM_LD32(s_addr + 96, sr, 96);
-      tmem_wait_ld();
-
-      const int rem = k_len - j * BLOCK_N;  // valid keys in this block
-      if (rem < BLOCK_N) {
-#pragma unroll
-        for (int c = 0; c < 128; ++c)
-          if (c >= rem) sr[c] = 0xff800000u;  // -inf
-      }
-      float m_blk = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 128; ++c) m_blk = fmaxf(m_blk, __uint_as_float(sr[c]));
-      const float m_new = fmaxf(m_used, m_blk);
-      if (j == 0) {
-        m_used = m_new;
-      } else {
-        const bool need = (m_new - m_used) * scale_log2 > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {
-          // O must be complete (P_{j-1} V_{j-1} done) before it is rescaled in place.
-          mbar_wait(&bars->pv_done, (j - 1) & 1);
+        issue_pv(0, st, j == 0);
+        if (has_next) {
+          mbar_wait(&bars->k_full[nst], ((j + 1) >> 1) & 1);
           tc_fence_after();
-          const float alpha = need ? fast_exp2((m_used - m_new) * scale_log2) : 1.f;
-          if (need) {
-            m_used = m_new;
-            l *= alpha;
-          }
-#pragma unroll
-          for (int c0 = 0; c0 < D; c0 += 32) {
-            uint32_t o[32];
-            HG_TMEM_LD32(tmem + lane_base + kTmemO + c0, o, 0);
-            tmem_wait_ld();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-            HG_TMEM_ST32(tmem + lane_base + kTmemO + c0, o, 0);
+          issue_qk(0, nst);
+          umma_commit(&bars->s_full[0]);
+        } else {
+          umma_commit(&bars->o_full[0]);
+        }
+        // ---- tile B
+        if (two) {
+          mbar_wait(&bars->p_full[1], j & 1);
+          tc_fence_after();
+          issue_pv(1, st, j == 0);
+        }
+        umma_commit(&bars->v_empty[st]);
+        if (two) {
+          if (has_next) {
+            issue_qk(1, nst);
+            umma_commit(&bars->s_full[1]);
+          } else {
+            umma_commit(&bars->o_full[1]);
           }
         }
+        if (has_next) umma_commit(&bars->k_empty[nst]);
       }
-      const float neg_mc = -m_used * scale_log2;
-      float psum = 0.f;
-      uint32_t pk[64];
-#pragma unroll
-      for (int c = 0; c < 128; c += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c]), scale_log2, neg_mc));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + 1]), scale_log2, neg_mc));
-        psum += p0 + p1;
-        pk[c / 2] = pack2<T>(p0, p1);
-      }
-      l += psum;
-      HG_TMEM_ST32(s_addr + 0, pk, 0);
-      HG_TMEM_ST32(s_addr + 32, pk, 32);
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&bars->p_full[buf]);
     }
+  }
+  } else {
+    // =============================== softmax / correction / epilogue ==========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    const int t = (warp - 4) >> 2;     // tile owned by this warpgroup
+    const int rows_valid = min(BLOCK_M, rows_left - t * BLOCK_M);
+    if (rows_valid > 0) {
+      const int wq = warp & 3;           // == warp % 4: the TMEM lane quarter this warp may access
+      const int row = wq * 32 + lane;    // row of the tile == TMEM lane
+      const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+      const uint32_t s_addr = tmem + lane_base + tmem_s(t);
+      const uint32_t o_addr = tmem + lane_base + tmem_o(t);
+      float m_used = -INFINITY;          // raw-score max the exponentials are referenced to
+      float l = 0.f;
 
-    // ---- epilogue --------------------------------------------------------------------------
-    mbar_wait(&bars->pv_done, (n_blocks - 1) & 1);
-    tc_fence_after();
-    const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
-    const bool row_ok = row < rows_valid;
-    T* orow = out + ((int64_t)(q_row0 + row) * hq + head) * D;
+      for (int j = 0; j < n_blocks; ++j) {
+        mbar_wait(&bars->s_full[t], j & 1);
+        tc_fence_after();
+        uint32_t sr[128];
+        HG_TMEM_LD32(s_addr + 0, sr, 0);
+        HG_TMEM_LD32(s_addr + 32, sr, 32);
+        HG_TMEM_LD32(s_addr + 64, sr, 64);
+        HG_TMEM_LD32(s_addr + 96, sr, 96);
+        tmem_wait_ld();
+
+        const int rem = k_len - j * BLOCK_N;  // valid keys in this block
+        if (rem < BLOCK_N) {
 #pragma unroll
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      uint32_t o[32];
-      HG_TMEM_LD32(tmem + lane_base + kTmemO + c0, o, 0);
-      tmem_wait_ld();
-      if (row_ok) {
+          for (int c = 0; c < 128; ++c)
+            if (c >= rem) sr[c] = 0xff800000u;  // -inf
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          uint4 w;
-          w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
-          w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
-          w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
-          w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
-          st_v4(orow + c0 + c, w);
+        for (int c = 0; c < 128; c += 4) {
+          mx[0] = fmaxf(mx[0], __uint_as_float(sr[c + 0]));
+          mx[1] = fmaxf(mx[1], __uint_as_float(sr[c + 1]));
+          mx[2] = fmaxf(mx[2], __uint_as_float(sr[c + 2]));
+          mx[3] = fmaxf(mx[3], __uint_as_float(sr[c + 3]));
+        }
+        const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        const float m_new = fmaxf(m_used, m_blk);
+        if (j == 0) {
+          m_used = m_new;
+        } else {
+          const bool need = (m_new - m_used) * scale_log2 > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {
+            // S_t(j) has arrived, so PV_t(j-1) has retired (commit order) and O_t is stable until
+            // this warpgroup releases P_t(j): rescale it in place.
+            const float alpha = need ? fast_exp2((m_used - m_new) * scale_log2) : 1.f;
+            if (need) {
+              m_used = m_new;
+              l *= alpha;
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < D; c0 += 32) {
+              uint32_t o[32];
+              HG_TMEM_LD32(o_addr + c0, o, 0);
+              tmem_wait_ld();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+              HG_TMEM_ST32(o_addr + c0, o, 0);
+            }
+          }
+        }
+        const float neg_mc = -m_used * scale_log2;
+        float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {  // 32 keys -> 16 packed columns of P, stored as soon as they exist
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(sr[ch * 32 + c]), scale_log2, neg_mc));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(sr[ch * 32 + c + 1]), scale_log2, neg_mc));
+            ps[(c >> 1) & 3] += p0 + p1;
+            pk[c >> 1] = pack2<T>(p0, p1);
+          }
+          HG_TMEM_ST16(s_addr + ch * 16, pk, 0);
+        }
+        l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bars->p_full[t]);
+      }
+
+      // ---- epilogue --------------------------------------------------------------------------
+      mbar_wait(&bars->o_full[t], 0);
+      tc_fence_after();
+      const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+      const int tile_row0 = q_row0 + t * BLOCK_M;
+      if (rows_valid == BLOCK_M) {
+        // full tile: O_t / l -> the (dead) Q_t tile in the TMA 128-byte swizzle -> one bulk store per
+        // 64-column half.  Row r keeps 16-byte chunk c at chunk slot c ^ (r & 7).
+        uint8_t* stage = smem + L::kQ + t * L::kTileBytes;
+#pragma unroll
+        for (int c0 = 0; c0 < D; c0 += 32) {
+          uint32_t o[32];
+          HG_TMEM_LD32(o_addr + c0, o, 0);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            uint4 w;
+            w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+            w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+            w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+            w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+            const int chunk = (c0 + c) >> 3;  // 16-byte chunk of the row
+            uint8_t* dst = stage + (chunk >> 3) * L::kHalfBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = w;
+          }
+        }
+        fence_proxy_async();
+        if (t == 0) named_bar_sync<1, BLOCK_M>(); else named_bar_sync<2, BLOCK_M>();
+        if (wq == 0 && lane == 0) {
+#pragma unroll
+          for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&tmap_o, stage + h * L::kHalfBytes, head * D + h * 64, tile_row0);
+          bulk_commit_and_wait();
+        }
+      } else {
+        const bool row_ok = row < rows_valid;
+        T* orow = out + ((int64_t)(tile_row0 + row) * hq + head) * D;
+#pragma unroll
+        for (int c0 = 0; c0 < D; c0 += 32) {
+          uint32_t o[32];
+          HG_TMEM_LD32(o_addr + c0, o, 0);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+              uint4 w;
+              w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+              w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+              w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+              w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+              st_v4(orow + c0 + c, w);
+            }
+          }
         }
       }
+      if (row < rows_valid && lse != nullptr)
+        lse[(int64_t)(tile_row0 + row) * hq + head] = (l > 0.f) ? (m_used * scale_log2 + fast_log2(l)) * kLn2 : -INFINITY;
+      tc_fence_before();
     }
-    if (row_ok && lse != nullptr)
-      lse[(int64_t)(q_row0 + row) * hq + head] = (l > 0.f) ? (m_used * scale_log2 + fast_log2(l)) * kLn2 : -INFINITY;
-    tc_fence_before();
   }
 
   // ---- teardown ----------------------------------------------------------------------------
@@ -461,7 +585,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D view [rows, cols] of a 16-bit tensor with row stride `row_stride` elements; boxes of 128 rows x 64 cols,
-// SWIZZLE_128B (a box row is exactly one 128-byte swizzle span), rows past `rows` read as zero.
+// SWIZZLE_128B (a box row is exactly one 128-byte swizzle span), rows past `rows` read as zero / are not written.
 static int make_tmap(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t row_stride) {
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(device_info().encode_tiled);
   if (fn == nullptr) return set_error(HG_ERR_NOT_INITIALIZED, "prefix: cuTensorMapEncodeTiled unavailable (call hg_init first)");
@@ -480,11 +604,12 @@ template <typename T, int D>
 static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) {
   using L = SmemLayout<D>;
   const int64_t n_q_rows = (int64_t)p.n_groups * p.q_per_group;
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk, tv, to;
   int rc;
   if ((rc = make_tmap(&tq, p.q, dtype, n_q_rows, (uint64_t)p.hq * D, p.q_stride_row)) != HG_OK) return rc;
   if ((rc = make_tmap(&tk, p.k, dtype, p.n_k_rows, (uint64_t)p.hkv * D, p.kv_stride_row)) != HG_OK) return rc;
   if ((rc = make_tmap(&tv, p.v, dtype, p.n_k_rows, (uint64_t)p.hkv * D, p.kv_stride_row)) != HG_OK) return rc;
+  if ((rc = make_tmap(&to, p.out, dtype, n_q_rows, (uint64_t)p.hq * D, (uint64_t)p.hq * D)) != HG_OK) return rc;
   const int smem_bytes = L::kTotal + 1024;
   static bool attr_set = false;  // per instantiation; idempotent, racing threads set the same value
   if (!attr_set) {
@@ -492,9 +617,9 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
     if (e != cudaSuccess) return set_error(HG_ERR_CUDA, "prefix: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int tiles_per_group = (p.q_per_group + BLOCK_M - 1) / BLOCK_M;
+  const int tiles_per_group = (p.q_per_group + kTiles * BLOCK_M - 1) / (kTiles * BLOCK_M);
   dim3 grid((unsigned)(p.n_groups * tiles_per_group), (unsigned)p.hq, 1);
-  prefix_attn_sm100_kernel<T, D><<<grid, kThreads, smem_bytes, s>>>(tq, tk, tv, (T*)p.out, p.lse, p.cu_seqlens_k, p.q_per_group,
+  prefix_attn_sm100_kernel<T, D><<<grid, kThreads, smem_bytes, s>>>(tq, tk, tv, to, (T*)p.out, p.lse, p.cu_seqlens_k, p.q_per_group,
                                                                      tiles_per_group, p.k_len, p.hq, p.hkv, p.scale_log2);
   return check_launch("prefix_attn_sm100");
 }
