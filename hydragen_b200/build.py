@@ -32,6 +32,13 @@ NVCC_FLAGS = [
 ]
 
 
+# development only: e.g. HG_EXTRA_NVCC_FLAGS="-DHG_PREFIX_TRACE" builds a separate, instrumented library
+EXTRA_FLAGS = os.environ.get("HG_EXTRA_NVCC_FLAGS", "").split()
+if EXTRA_FLAGS:
+    OUT_DIR = os.path.join(PKG_DIR, "_C_dev")
+    LIB_PATH = os.path.join(OUT_DIR, "libhydragen_b200.so")
+
+
 def _nvcc() -> str:
     cand = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(cand):
@@ -44,6 +51,7 @@ def _stamp() -> str:
     for path in [os.path.join(CSRC, s) for s in SOURCES] + HEADERS + [os.path.abspath(__file__)]:
         with open(path, "rb") as f:
             h.update(f.read())
+    h.update(" ".join(EXTRA_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -65,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *EXTRA_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(OUT_DIR, src + ".log")
         with open(log, "w") as f:

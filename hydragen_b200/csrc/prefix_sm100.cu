@@ -43,12 +43,12 @@ namespace hg {
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_N = 128;
+constexpr int BLOCK_N = 64;   // keys per block: S_t block = 64 TMEM columns, double buffered
 constexpr int kTiles = 2;  // Q tiles per CTA (ping-pong)
 constexpr int kThreads = 384;
 constexpr uint32_t kTmemCols = 512;
-__host__ __device__ constexpr uint32_t tmem_s(int t) { return (uint32_t)t * 128u; }        // S_t (P_t aliases its first 64 columns)
-__host__ __device__ constexpr uint32_t tmem_o(int t) { return 256u + (uint32_t)t * 128u; }  // O_t
+__host__ __device__ constexpr uint32_t tmem_s(int t, int b) { return (uint32_t)t * 128u + (uint32_t)b * 64u; }  // S_t buffer b (P aliases its first 32 columns)
+__host__ __device__ constexpr uint32_t tmem_o(int t) { return 256u + (uint32_t)t * 128u; }                       // O_t
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -225,26 +225,49 @@ __device__ __forceinline__ void named_bar_sync() {
   asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(THREADS) : "memory");
 }
 
+constexpr int kStages = 4;  // K/V ring depth
+
+// Ring slot u (u = -2 .. n_blocks-1) holds what MMA iteration u consumes: V_u (for P V of block u)
+// and K_{u+2} (for Q K^T of block u+2, issued in the same iteration); slots -2 and -1 carry only
+// K_0 / K_1 for the prologue.  One full and one empty barrier per slot.
 template <int D>
 struct SmemLayout {
-  static constexpr int kHalves = D / 64;                 // 64-element (128-byte) swizzle atoms along d
-  static constexpr int kTileBytes = BLOCK_N * D * 2;     // one Q / K / V tile
-  static constexpr int kHalfBytes = BLOCK_N * 64 * 2;    // one TMA box: 128 rows x 128 B
-  static constexpr int kQ = 0;                           // 2 tiles (A, B); reused as the output staging tiles
-  static constexpr int kK = kTileBytes * 2;              // 2 stages
-  static constexpr int kV = kTileBytes * 4;              // 2 stages
-  static constexpr int kBars = kTileBytes * 6;
-  static constexpr int kTotal = kBars + 256;
+  static constexpr int kHalves = D / 64;                    // 64-element (128-byte) swizzle atoms along d
+  static constexpr int kQTileBytes = BLOCK_M * D * 2;       // one Q tile (also one output staging tile)
+  static constexpr int kQHalfBytes = BLOCK_M * 64 * 2;      // one Q TMA box: 128 rows x 128 B
+  static constexpr int kKVTileBytes = BLOCK_N * D * 2;      // one K / V block
+  static constexpr int kKVHalfBytes = BLOCK_N * 64 * 2;     // one K/V TMA box: 64 rows x 128 B
+  static constexpr int kStageBytes = 2 * kKVTileBytes;      // V block then K block
+  static constexpr int kQ = 0;                              // 2 tiles (A, B)
+  static constexpr int kKV = kQTileBytes * kTiles;
+  static constexpr int kBars = kKV + kStageBytes * kStages;
+  static constexpr int kTotal = kBars + 512;
 };
 
 struct Barriers {
   uint64_t q_full[kTiles];
-  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
-  uint64_t s_full[kTiles], p_full[kTiles], o_full[kTiles];
+  uint64_t kv_full[kStages], kv_empty[kStages];
+  uint64_t s_full[kTiles][2], p_full[kTiles][2];  // per S buffer
+  uint64_t pv_done[kTiles];                       // one phase per PV_t(j) (lazy-rescale path only)
+  uint64_t o_full[kTiles];                        // O_t complete
   uint32_t tmem_base;
 };
 
 }  // namespace
+
+#ifdef HG_PREFIX_TRACE
+// Development aid (never compiled into the shipped library): clock64 stamps of CTA (0,0).
+// Layout: [role][block j][slot]; role 0 = MMA thread, 1 = softmax warp of tile A, 2 = tile B.
+__device__ long long g_trace[3 * 64 * 8];
+#define HG_TRACE(role, j, slot)                                                                              \
+  do {                                                                                                       \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (j) < 64) g_trace[((role) * 64 + (j)) * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define HG_TRACE(role, j, slot) \
+  do {                          \
+  } while (0)
+#endif
 
 template <typename T, int D>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -297,15 +320,18 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kTiles; ++i) {
       mbar_init(&bars->q_full[i], 1);
-      mbar_init(&bars->k_full[i], 1);
-      mbar_init(&bars->k_empty[i], 1);
-      mbar_init(&bars->v_full[i], 1);
-      mbar_init(&bars->v_empty[i], 1);
-      mbar_init(&bars->s_full[i], 1);
-      mbar_init(&bars->p_full[i], BLOCK_M);
+      mbar_init(&bars->pv_done[i], 1);
       mbar_init(&bars->o_full[i], 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bars->s_full[i][b], 1);
+        mbar_init(&bars->p_full[i][b], BLOCK_M);
+      }
+    }
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bars->kv_full[i], 1);
+      mbar_init(&bars->kv_empty[i], two ? 2 : 1);  // one tcgen05.commit per MMA warp
     }
     fence_barrier_init();
   }
@@ -329,102 +355,105 @@ __global__ void __launch_bounds__(kThreads, 1)
     // =============================== TMA producer ===========================================
     if (elect_one()) {
       for (int t = 0; t < (two ? 2 : 1); ++t) {
-        mbar_expect_tx(&bars->q_full[t], L::kTileBytes);
+        mbar_expect_tx(&bars->q_full[t], L::kQTileBytes);
 #pragma unroll
         for (int h = 0; h < L::kHalves; ++h)
-          tma_load_2d(smem + L::kQ + t * L::kTileBytes + h * L::kHalfBytes, &tmap_q, head * D + h * 64, q_row0 + t * BLOCK_M,
+          tma_load_2d(smem + L::kQ + t * L::kQTileBytes + h * L::kQHalfBytes, &tmap_q, head * D + h * 64, q_row0 + t * BLOCK_M,
                       &bars->q_full[t]);
       }
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int row = k_start + j * BLOCK_N;
-        mbar_wait(&bars->k_empty[st], ph ^ 1);
-        mbar_expect_tx(&bars->k_full[st], L::kTileBytes);
+      for (int u = -2; u < n_blocks; ++u) {
+        const int st = (u + 2) % kStages;
+        const bool has_v = u >= 0, has_k = u + 2 < n_blocks;
+        if (!has_v && !has_k) continue;
+        uint8_t* base = smem + L::kKV + st * L::kStageBytes;
+        mbar_wait(&bars->kv_empty[st], (((u + 2) / kStages) & 1) ^ 1);
+        mbar_expect_tx(&bars->kv_full[st], (has_v ? L::kKVTileBytes : 0) + (has_k ? L::kKVTileBytes : 0));
+        if (has_k) {
 #pragma unroll
-        for (int h = 0; h < L::kHalves; ++h)
-          tma_load_2d(smem + L::kK + st * L::kTileBytes + h * L::kHalfBytes, &tmap_k, kvh * D + h * 64, row, &bars->k_full[st]);
-        mbar_wait(&bars->v_empty[st], ph ^ 1);
-        mbar_expect_tx(&bars->v_full[st], L::kTileBytes);
+          for (int h = 0; h < L::kHalves; ++h)
+            tma_load_2d(base + L::kKVTileBytes + h * L::kKVHalfBytes, &tmap_k, kvh * D + h * 64, k_start + (u + 2) * BLOCK_N,
+                        &bars->kv_full[st]);
+        }
+        if (has_v) {
 #pragma unroll
-        for (int h = 0; h < L::kHalves; ++h)
-          tma_load_2d(smem + L::kV + st * L::kTileBytes + h * L::kHalfBytes, &tmap_v, kvh * D + h * 64, row, &bars->v_full[st]);
+          for (int h = 0; h < L::kHalves; ++h)
+            tma_load_2d(base + h * L::kKVHalfBytes, &tmap_v, kvh * D + h * 64, k_start + u * BLOCK_N, &bars->kv_full[st]);
+        }
       }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer =============================================
-    if (elect_one()) {
-      // S_t = Q_t K^T: D/16 instructions of 128x128x16; operand k-slice kk lives in swizzle atom kk/4
+  } else if (warp == 1 || warp == 3) {
+    // =============================== MMA issuers (warp 1: tile A, warp 3: tile B) ==============
+    // The whole warp walks the loop and the barriers (warp-uniform, so descriptors stay in uniform
+    // registers); one elected lane issues tcgen05.mma / tcgen05.commit.  Per block j and tile t:
+    //   P V of block j, then Q K^T of block j+2 into the S buffer P_t(j) just vacated (same thread,
+    //   same issue order: no barrier needed between them).
+    const int t = warp >> 1;
+    if (t == 0 || two) {
+      const bool leader = elect_one();
+      constexpr uint32_t kHiK = desc_hi(1024);  // SWIZZLE_128B: 8-row groups 1024 B apart
+      const uint32_t q_lo = desc_lo(smem_u32(smem + L::kQ + t * L::kQTileBytes), 0);
+      const uint32_t v_lo0 = desc_lo(smem_u32(smem + L::kKV), L::kKVHalfBytes);
+      const uint32_t k_lo0 = desc_lo(smem_u32(smem + L::kKV + L::kKVTileBytes), 0);
+      const uint32_t o_tmem = tmem + tmem_o(t);
+      // S_t = Q_t K^T: D/16 instructions of 128x64x16; operand k-slice kk lives in swizzle atom kk/4
       // at byte offset (kk%4)*32 inside the 128-byte row (start-address field is in 16-byte units).
-      constexpr uint32_t kHiK = desc_hi(1024);  // K-major SWIZZLE_128B: 8-row groups 1024 B apart
-      const uint32_t q_lo0 = desc_lo(smem_u32(smem + L::kQ), 0);
-      const uint32_t k_lo0 = desc_lo(smem_u32(smem + L::kK), 0);
-      const uint32_t v_lo0 = desc_lo(smem_u32(smem + L::kV), L::kHalfBytes);
-      auto issue_qk = [&](int t, int st) {
-        const uint32_t q_lo = q_lo0 + t * (L::kTileBytes >> 4);
-        const uint32_t k_lo = k_lo0 + st * (L::kTileBytes >> 4);
+      auto issue_qk = [&](int st, int sbuf) {
+        const uint32_t k_lo = k_lo0 + st * (L::kStageBytes >> 4);
+        const uint32_t d_tmem = tmem + tmem_s(t, sbuf);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = ((kk / 4) * L::kHalfBytes + (kk % 4) * 32) >> 4;
-          umma_ss(tmem + tmem_s(t), q_lo + off, kHiK, k_lo + off, kHiK, kIdescQK, kk > 0 ? 1u : 0u);
+          const uint32_t q_off = ((kk / 4) * L::kQHalfBytes + (kk % 4) * 32) >> 4;
+          const uint32_t k_off = ((kk / 4) * L::kKVHalfBytes + (kk % 4) * 32) >> 4;
+          umma_ss(d_tmem, q_lo + q_off, kHiK, k_lo + k_off, kHiK, kIdescQK, kk > 0 ? 1u : 0u);
         }
       };
       // O_t (+)= P_t V: BLOCK_N/16 instructions of 128xDx16; A = P_t (16-bit, 8 TMEM columns per
       // k-slice), B = V tile rows [kk*16, kk*16+16) as an MN-major operand: 8-row groups 1024 B apart
       // (SBO), 64-element column halves one TMA box apart (LBO).
-      auto issue_pv = [&](int t, int st, bool first) {
-        const uint32_t v_lo = v_lo0 + st * (L::kTileBytes >> 4);
+      auto issue_pv = [&](int st, int sbuf, bool first) {
+        const uint32_t v_lo = v_lo0 + st * (L::kStageBytes >> 4);
+        const uint32_t p_tmem = tmem + tmem_s(t, sbuf);
 #pragma unroll
-        for (int kk = 0; kk < BLOCK_N / 16; ++kk) {
-          umma_ts(tmem + tmem_o(t), tmem + tmem_s(t) + kk * 8, v_lo + kk * (2048 >> 4), kHiK, kIdescPV, (first && kk == 0) ? 0u : 1u);
-        }
+        for (int kk = 0; kk < BLOCK_N / 16; ++kk)
+          umma_ts(o_tmem, p_tmem + kk * 8, v_lo + kk * (2048 >> 4), kHiK, kIdescPV, (first && kk == 0) ? 0u : 1u);
       };
 
-      mbar_wait(&bars->q_full[0], 0);
-      mbar_wait(&bars->k_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      umma_commit(&bars->s_full[0]);
-      if (two) {
-        mbar_wait(&bars->q_full[1], 0);
-        tc_fence_after();
-        issue_qk(1, 0);
-        umma_commit(&bars->s_full[1]);
-      }
-      umma_commit(&bars->k_empty[0]);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j & 1, nst = st ^ 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const bool has_next = j + 1 < n_blocks;
-        // ---- tile A: PV_A(j), then QK_A(j+1) while softmax B(j) is still running
-        mbar_wait(&bars->p_full[0], j & 1);
-        mbar_wait(&bars->v_full[st], ph);
-        tc_fence_after();
-        issue_pv(0, st, j == 0);
-        if (has_next) {
-          mbar_wait(&bars->k_full[nst], ((j + 1) >> 1) & 1);
+      // prologue: S_t(0), S_t(1) -- the softmax warpgroup then always finds its next block ready
+      mbar_wait(&bars->q_full[t], 0);
+      for (int u = -2; u < 0; ++u) {
+        if (u + 2 < n_blocks) {
+          const int st = (u + 2) % kStages;
+          mbar_wait(&bars->kv_full[st], 0);
           tc_fence_after();
-          issue_qk(0, nst);
-          umma_commit(&bars->s_full[0]);
-        } else {
-          umma_commit(&bars->o_full[0]);
-        }
-        // ---- tile B
-        if (two) {
-          mbar_wait(&bars->p_full[1], j & 1);
-          tc_fence_after();
-          issue_pv(1, st, j == 0);
-        }
-        umma_commit(&bars->v_empty[st]);
-        if (two) {
-          if (has_next) {
-            issue_qk(1, nst);
-            umma_commit(&bars->s_full[1]);
-          } else {
-            umma_commit(&bars->o_full[1]);
+          if (leader) {
+            issue_qk(st, (u + 2) & 1);
+            umma_commit(&bars->s_full[t][(u + 2) & 1]);
+            umma_commit(&bars->kv_empty[st]);
           }
+          __syncwarp();
         }
-        if (has_next) umma_commit(&bars->k_empty[nst]);
+      }
+      for (int j = 0; j < n_blocks; ++j) {
+        const int b = j & 1;
+        const int st = (j + 2) % kStages;
+        const bool more = j + 2 < n_blocks;
+        if (t == 0) HG_TRACE(0, j, 0);
+        mbar_wait(&bars->kv_full[st], ((j + 2) / kStages) & 1);
+        if (t == 0) HG_TRACE(0, j, 1);
+        mbar_wait(&bars->p_full[t][b], (j >> 1) & 1);
+        if (t == 0) HG_TRACE(0, j, 2);
+        tc_fence_after();
+        if (leader) {
+          issue_pv(st, b, j == 0);
+          umma_commit(j + 1 < n_blocks ? &bars->pv_done[t] : &bars->o_full[t]);
+          if (more) {
+            issue_qk(st, b);
+            umma_commit(&bars->s_full[t][b]);
+          }
+          umma_commit(&bars->kv_empty[st]);
+        }
+        __syncwarp();
+        if (t == 0) HG_TRACE(0, j, 3);
       }
     }
   }
@@ -437,44 +466,49 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int wq = warp & 3;           // == warp % 4: the TMEM lane quarter this warp may access
       const int row = wq * 32 + lane;    // row of the tile == TMEM lane
       const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-      const uint32_t s_addr = tmem + lane_base + tmem_s(t);
       const uint32_t o_addr = tmem + lane_base + tmem_o(t);
       float m_used = -INFINITY;          // raw-score max the exponentials are referenced to
       float l = 0.f;
 
-      for (int j = 0; j < n_blocks; ++j) {
-        mbar_wait(&bars->s_full[t], j & 1);
-        tc_fence_after();
-        uint32_t sr[128];
-        HG_TMEM_LD32(s_addr + 0, sr, 0);
-        HG_TMEM_LD32(s_addr + 32, sr, 32);
-        HG_TMEM_LD32(s_addr + 64, sr, 64);
-        HG_TMEM_LD32(s_addr + 96, sr, 96);
-        tmem_wait_ld();
+      // Software pipeline over key blocks.  Per block the warp issues 64 MUFU exp2; everything else it
+      // has to do -- the scale FFMAs, the row sums and the 16-bit packing of block j, and (once S_t(j+1)
+      // can have landed: its Q K^T is only issued after P_t(j-1) was consumed) fetching the scores of
+      // block j+1 from TMEM and reducing them to their row max -- is written interleaved with those MUFU
+      // requests in groups of 8, so that the in-order warp always has independent work behind them and
+      // the two softmax warps sharing an SM sub-partition do not convoy on the MUFU unit.  Two score
+      // register arrays alternate between "being exponentiated" and "being fetched".
+      uint32_t sa[BLOCK_N], sb[BLOCK_N];
+      float m_blk;
+      auto mask_tail = [&](uint32_t(&x)[BLOCK_N], int j) {
+        const int rem = k_len - j * BLOCK_N;
+#pragma unroll
+        for (int c = 0; c < BLOCK_N; ++c)
+          if (c >= rem) x[c] = 0xff800000u;  // -inf
+      };
+      auto max8 = [&](float* mx, const uint32_t(&x)[BLOCK_N], int g) {
+        mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(x[g * 8 + 0]), __uint_as_float(x[g * 8 + 1])));
+        mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(x[g * 8 + 2]), __uint_as_float(x[g * 8 + 3])));
+        mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(x[g * 8 + 4]), __uint_as_float(x[g * 8 + 5])));
+        mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(x[g * 8 + 6]), __uint_as_float(x[g * 8 + 7])));
+      };
 
-        const int rem = k_len - j * BLOCK_N;  // valid keys in this block
-        if (rem < BLOCK_N) {
-#pragma unroll
-          for (int c = 0; c < 128; ++c)
-            if (c >= rem) sr[c] = 0xff800000u;  // -inf
-        }
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int c = 0; c < 128; c += 4) {
-          mx[0] = fmaxf(mx[0], __uint_as_float(sr[c + 0]));
-          mx[1] = fmaxf(mx[1], __uint_as_float(sr[c + 1]));
-          mx[2] = fmaxf(mx[2], __uint_as_float(sr[c + 2]));
-          mx[3] = fmaxf(mx[3], __uint_as_float(sr[c + 3]));
-        }
-        const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      // cur: scores of block j (masked, max known in m_blk); nxt: receives block j+1.
+      // kHasNext: block j+1 exists; kMaskNext: it is the ragged last block.
+      auto body = [&](int j, uint32_t(&cur)[BLOCK_N], uint32_t(&nxt)[BLOCK_N], auto has_next_tag, auto mask_next_tag) {
+        constexpr bool kHasNext = decltype(has_next_tag)::value;
+        constexpr bool kMaskNext = decltype(mask_next_tag)::value;
+        const uint32_t p_addr = tmem + lane_base + tmem_s(t, j & 1);
+        if (wq == 0 && lane == 0) HG_TRACE(1 + t, j, 1);
         const float m_new = fmaxf(m_used, m_blk);
         if (j == 0) {
           m_used = m_new;
         } else {
           const bool need = (m_new - m_used) * scale_log2 > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) {
-            // S_t(j) has arrived, so PV_t(j-1) has retired (commit order) and O_t is stable until
-            // this warpgroup releases P_t(j): rescale it in place.
+            // rare: O_t must be complete up to P_t(j-1) V_{j-1} before it is rescaled in place; P_t(j)
+            // has not been released yet, so no later MMA can be touching O_t.
+            mbar_wait(&bars->pv_done[t], (j - 1) & 1);
+            tc_fence_after();
             const float alpha = need ? fast_exp2((m_used - m_new) * scale_log2) : 1.f;
             if (need) {
               m_used = m_new;
@@ -493,22 +527,88 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         const float neg_mc = -m_used * scale_log2;
         float ps[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[BLOCK_N / 2];
+        auto exp8 = [&](int g) {  // in place: score -> p
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {  // 32 keys -> 16 packed columns of P, stored as soon as they exist
-          uint32_t pk[16];
+          for (int c = 0; c < 8; ++c)
+            cur[g * 8 + c] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(cur[g * 8 + c]), scale_log2, neg_mc)));
+        };
+        auto sum_pack8 = [&](int g) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(sr[ch * 32 + c]), scale_log2, neg_mc));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(sr[ch * 32 + c + 1]), scale_log2, neg_mc));
+          for (int c = 0; c < 8; c += 2) {
+            const float p0 = __uint_as_float(cur[g * 8 + c]), p1 = __uint_as_float(cur[g * 8 + c + 1]);
             ps[(c >> 1) & 3] += p0 + p1;
-            pk[c >> 1] = pack2<T>(p0, p1);
+            pk[(g * 8 + c) >> 1] = pack2<T>(p0, p1);
           }
-          HG_TMEM_ST16(s_addr + ch * 16, pk, 0);
+        };
+#pragma unroll
+        for (int g = 0; g < 6; ++g) {
+          exp8(g);
+          if (g >= 2) sum_pack8(g - 2);
+        }
+        HG_TMEM_ST16(p_addr, pk, 0);  // keys 0..31 of P
+        if (wq == 0 && lane == 0) HG_TRACE(1 + t, j, 2);
+        if constexpr (kHasNext) {     // S_t(j+1) has had ~3/4 of this block's MUFU time to land
+          mbar_wait(&bars->s_full[t][(j + 1) & 1], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          const uint32_t s_addr = tmem + lane_base + tmem_s(t, (j + 1) & 1);
+          HG_TMEM_LD32(s_addr + 0, nxt, 0);
+          HG_TMEM_LD32(s_addr + 32, nxt, 32);
+        }
+        if (wq == 0 && lane == 0) HG_TRACE(1 + t, j, 3);
+        exp8(6);
+        sum_pack8(4);
+        exp8(7);
+        sum_pack8(5);
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if constexpr (kHasNext) {
+          tmem_wait_ld();
+          if constexpr (kMaskNext) mask_tail(nxt, j + 1);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) max8(mx, nxt, g);
+        }
+        sum_pack8(6);
+        sum_pack8(7);
+        HG_TMEM_ST16(p_addr + 16, pk, 16);
+        if constexpr (kHasNext) {
+#pragma unroll
+          for (int g = 4; g < 8; ++g) max8(mx, nxt, g);
+          m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
         }
         l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+        if (wq == 0 && lane == 0) HG_TRACE(1 + t, j, 4);
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&bars->p_full[t]);
+        mbar_arrive(&bars->p_full[t][j & 1]);
+        if (wq == 0 && lane == 0) HG_TRACE(1 + t, j, 5);
+      };
+
+      {  // prologue: scores and row max of block 0
+        if (wq == 0 && lane == 0) HG_TRACE(1 + t, 0, 0);
+        mbar_wait(&bars->s_full[t][0], 0);
+        tc_fence_after();
+        const uint32_t s_addr = tmem + lane_base + tmem_s(t, 0);
+        HG_TMEM_LD32(s_addr + 0, sa, 0);
+        HG_TMEM_LD32(s_addr + 32, sa, 32);
+        tmem_wait_ld();
+        if (k_len < BLOCK_N) mask_tail(sa, 0);
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int g = 0; g < 8; ++g) max8(mx, sa, g);
+        m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      }
+      const bool ragged = (k_len % BLOCK_N) != 0;
+      for (int j = 0; j < n_blocks; ++j) {
+        const bool last = j + 1 == n_blocks, mask_next = ragged && (j + 2 == n_blocks);
+        if ((j & 1) == 0) {
+          if (last) body(j, sa, sb, std::false_type{}, std::false_type{});
+          else if (mask_next) body(j, sa, sb, std::true_type{}, std::true_type{});
+          else body(j, sa, sb, std::true_type{}, std::false_type{});
+        } else {
+          if (last) body(j, sb, sa, std::false_type{}, std::false_type{});
+          else if (mask_next) body(j, sb, sa, std::true_type{}, std::true_type{});
+          else body(j, sb, sa, std::true_type{}, std::false_type{});
+        }
       }
 
       // ---- epilogue --------------------------------------------------------------------------
@@ -519,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (rows_valid == BLOCK_M) {
         // full tile: O_t / l -> the (dead) Q_t tile in the TMA 128-byte swizzle -> one bulk store per
         // 64-column half.  Row r keeps 16-byte chunk c at chunk slot c ^ (r & 7).
-        uint8_t* stage = smem + L::kQ + t * L::kTileBytes;
+        uint8_t* stage = smem + L::kQ + t * L::kQTileBytes;
 #pragma unroll
         for (int c0 = 0; c0 < D; c0 += 32) {
           uint32_t o[32];
@@ -533,7 +633,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
             w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
             const int chunk = (c0 + c) >> 3;  // 16-byte chunk of the row
-            uint8_t* dst = stage + (chunk >> 3) * L::kHalfBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+            uint8_t* dst = stage + (chunk >> 3) * L::kQHalfBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
             *reinterpret_cast<uint4*>(dst) = w;
           }
         }
@@ -541,7 +641,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (t == 0) named_bar_sync<1, BLOCK_M>(); else named_bar_sync<2, BLOCK_M>();
         if (wq == 0 && lane == 0) {
 #pragma unroll
-          for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&tmap_o, stage + h * L::kHalfBytes, head * D + h * 64, tile_row0);
+          for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&tmap_o, stage + h * L::kQHalfBytes, head * D + h * 64, tile_row0);
           bulk_commit_and_wait();
         }
       } else {
@@ -584,14 +684,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// 2-D view [rows, cols] of a 16-bit tensor with row stride `row_stride` elements; boxes of 128 rows x 64 cols,
+// 2-D view [rows, cols] of a 16-bit tensor with row stride `row_stride` elements; boxes of box_rows rows x 64 cols,
 // SWIZZLE_128B (a box row is exactly one 128-byte swizzle span), rows past `rows` read as zero / are not written.
-static int make_tmap(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t row_stride) {
+static int make_tmap(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t row_stride,
+                     uint32_t box_rows) {
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(device_info().encode_tiled);
   if (fn == nullptr) return set_error(HG_ERR_NOT_INITIALIZED, "prefix: cuTensorMapEncodeTiled unavailable (call hg_init first)");
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {row_stride * 2};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, dtype == HG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -606,10 +707,10 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   const int64_t n_q_rows = (int64_t)p.n_groups * p.q_per_group;
   CUtensorMap tq, tk, tv, to;
   int rc;
-  if ((rc = make_tmap(&tq, p.q, dtype, n_q_rows, (uint64_t)p.hq * D, p.q_stride_row)) != HG_OK) return rc;
-  if ((rc = make_tmap(&tk, p.k, dtype, p.n_k_rows, (uint64_t)p.hkv * D, p.kv_stride_row)) != HG_OK) return rc;
-  if ((rc = make_tmap(&tv, p.v, dtype, p.n_k_rows, (uint64_t)p.hkv * D, p.kv_stride_row)) != HG_OK) return rc;
-  if ((rc = make_tmap(&to, p.out, dtype, n_q_rows, (uint64_t)p.hq * D, (uint64_t)p.hq * D)) != HG_OK) return rc;
+  if ((rc = make_tmap(&tq, p.q, dtype, n_q_rows, (uint64_t)p.hq * D, p.q_stride_row, BLOCK_M)) != HG_OK) return rc;
+  if ((rc = make_tmap(&tk, p.k, dtype, p.n_k_rows, (uint64_t)p.hkv * D, p.kv_stride_row, BLOCK_N)) != HG_OK) return rc;
+  if ((rc = make_tmap(&tv, p.v, dtype, p.n_k_rows, (uint64_t)p.hkv * D, p.kv_stride_row, BLOCK_N)) != HG_OK) return rc;
+  if ((rc = make_tmap(&to, p.out, dtype, n_q_rows, (uint64_t)p.hq * D, (uint64_t)p.hq * D, BLOCK_M)) != HG_OK) return rc;
   const int smem_bytes = L::kTotal + 1024;
   static bool attr_set = false;  // per instantiation; idempotent, racing threads set the same value
   if (!attr_set) {
@@ -623,6 +724,13 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
                                                                      tiles_per_group, p.k_len, p.hq, p.hkv, p.scale_log2);
   return check_launch("prefix_attn_sm100");
 }
+
+#ifdef HG_PREFIX_TRACE
+extern "C" int hg_debug_read_trace(long long* host_buf, int n) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host_buf, g_trace, sizeof(long long) * (size_t)n);
+}
+#endif
 
 int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
   if (p.n_groups == 0 || p.q_per_group == 0) return HG_OK;
