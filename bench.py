@@ -10,8 +10,9 @@ B = 1024 sequences decoding one token each against ONE shared prefix of 2048 tok
 sequence owning `--suffix-len` tokens of its own KV (default 1), 32 query / 32 kv heads, d = 128,
 bf16.  One STEP = the attention hot path of one whole-model decode step: for each of the 32 layers
 (each with its OWN caches, so 1.5 GB+ of distinct inputs stream through the 126 MB L2 per step)
-    KV append of the new token  ->  prefix attention (tcgen05)  ->  suffix attention + combine
-i.e. ``hydragen_attention`` called exactly as hydragen/llama.py:564-587 of the reference calls it.
+    prefix attention (tcgen05)  ->  ONE launch: KV append of the new token + suffix attention + combine
+i.e. what the reference's decode branch does with update_per_completion_kvs + hydragen_attention
+(hydragen/llama.py:564-587), through ``hydragen_attention_decode``.
 The step is captured in a CUDA graph (the reference replays graphs too: llama.py:781-866,
 benchmark_utils.py:140-170).  `value` = B / step time = decode tokens/s of the attention path
 (the projections / MLP / sampling around it are out of scope: SURVEY.md section 8).
@@ -213,8 +214,8 @@ def run_ours(a):
         dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=dev)
 
     from hydragen_b200 import _lib
-    from hydragen_b200.attention import hydragen_attention_nopad
-    from hydragen_b200.flash import prefix_attention_grouped
+    from hydragen_b200.attention import hydragen_attention_decode
+    from hydragen_b200.flash import decode_attention_fused, prefix_attention_grouped
 
     _lib.load()  # raises if the CUDA extension is missing: no fallback
     assert a.heads % world == 0 and a.kv_heads % world == 0, "heads must divide over the ranks (hydragen/tp.py:43-46)"
@@ -237,8 +238,8 @@ def run_ours(a):
     outs = [None] * L
 
     def layer(i):
-        _lib.kv_append(kn[i], vn[i], pos, uniq[i, 0], uniq[i, 1])
-        outs[i] = hydragen_attention_nopad(qs[i], uniq[i, 0], uniq[i, 1], [shared_k[i]], [shared_v[i]], seq_len=seq_lens)
+        # prefix launch (tcgen05) + ONE launch for KV append + suffix attention + combine
+        outs[i] = hydragen_attention_decode(qs[i], kn[i], vn[i], pos, uniq[i, 0], uniq[i, 1], [shared_k[i]], [shared_v[i]])
         if world > 1:
             dist.all_reduce(proj[i])  # the one collective per attention layer (hydragen/tp.py:108-112)
 
@@ -246,7 +247,7 @@ def run_ours(a):
         for i in range(L):
             layer(i)
 
-    launches_per_step = L * 3  # kv_append + prefix + fused suffix/combine (NCCL kernels not counted)
+    launches_per_step = L * 2  # prefix + fused append/suffix/combine (NCCL kernels not counted)
 
     for _ in range(3):
         step_eager()
@@ -303,8 +304,6 @@ def run_ours(a):
     tf_peak = float(peaks.get("bf16_tflops", 1590.0))
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json, burst)" if peaks else "fallback (B200_PROFILING.md)"
-    from hydragen_b200.flash import suffix_attention_fused
-
     # Per-kernel time, live: a CUDA graph holding ONLY that kernel's launches of one step (one per layer, each
     # on its own layer's tensors so nothing is L2-warm from a previous launch), replayed and timed with CUDA
     # events on the launching stream.  (Events around eager launches would time the Python launch gaps.)
@@ -316,7 +315,7 @@ def run_ours(a):
 
     def only_suffix():
         for i in range(L):
-            suffix_attention_fused(qs[i], uniq[i, 0], uniq[i, 1], seq_lens, causal=False, partial_outs=[pre_out[i][0]], partial_lses=[pre_out[i][1]])
+            decode_attention_fused(qs[i], kn[i], vn[i], pos, uniq[i, 0], uniq[i, 1], [pre_out[i][0]], [pre_out[i][1]])
 
     def time_kernel_graph(fn, reps=20):
         fn()
@@ -339,11 +338,12 @@ def run_ours(a):
     suf_t = time_kernel_graph(only_suffix)
     pre_flops = 4.0 * B * H * a.prefix_len * D
     esz = 2
-    suf_bytes = 2.0 * B * a.suffix_len * HKV * D * esz + 3.0 * B * H * D * esz + 2.0 * B * H * 4  # K,V + q,partial,out + 2 lse
+    # new K,V rows read + appended, older K,V rows read, q + prefix partial + out, 2 LSE rows
+    suf_bytes = 4.0 * B * HKV * D * esz + 2.0 * B * (a.suffix_len - 1) * HKV * D * esz + 3.0 * B * H * D * esz + 2.0 * B * H * 4
     roofline = {"kernel": "prefix_attn_sm100_kernel (tcgen05)", "bound": "tensor", "achieved": pre_flops / pre_t / 1e6, "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": pre_flops / pre_t / 1e6 / tf_peak, "traffic": None, "us_per_launch": pre_t,
                 "algorithmic_flop_per_launch": pre_flops, "peak_source": peak_src}
-    roofline_suffix = {"kernel": "decode_slot_kernel (suffix + combine)", "bound": "hbm", "achieved": suf_bytes / suf_t / 1e3, "peak": hbm_peak,
+    roofline_suffix = {"kernel": "decode_slot_kernel (kv append + suffix + combine)", "bound": "hbm", "achieved": suf_bytes / suf_t / 1e3, "peak": hbm_peak,
                        "unit": "GB/s", "frac": suf_bytes / suf_t / 1e3 / hbm_peak, "traffic": None, "us_per_launch": suf_t,
                        "algorithmic_bytes_per_launch": suf_bytes, "peak_source": peak_src}
     prof = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch read from the committed ncu --set full capture
@@ -401,7 +401,7 @@ def run_ours(a):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(a), "scope": "attention hot path of one decode step (kv append + prefix + suffix + combine per layer); projections/MLP/sampling out of scope",
+            "config": {"workload": workload_name(a), "scope": "attention hot path of one decode step (prefix + fused kv-append/suffix/combine per layer); projections/MLP/sampling out of scope",
                        "parallelism": f"tp{world} (head axis, 1 NCCL all-reduce of [B,{hidden}] bf16 per layer)" if world > 1 else "single GPU",
                        "l2": f"inputs larger than L2: {L} layers x distinct caches cycle {L * (2 * a.prefix_len * HKV * D * 2 + 4 * B * H * D * 2) / 2**20:.0f}+ MiB per step through a 126 MB L2",
                        "cuda_graph": graph is not None},

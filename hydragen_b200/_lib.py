@@ -41,6 +41,12 @@ SYMBOLS = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
          c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_void_p],
     ),
+    "hg_decode_attn_fused": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64,
+         _c_void_pp, _c_void_pp, c_int, c_float, c_int, c_void_p],
+    ),
     "hg_kv_append": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
@@ -182,3 +188,22 @@ def kv_append(k_new, v_new, positions, k_cache, v_cache) -> None:
         rc = load().hg_kv_append(_ptr(k_new), _ptr(v_new), _ptr(positions), pi64, _ptr(k_cache), _ptr(v_cache),
                                  b, nq, lk, hkv, d, dtype_code(k_new.dtype), _stream(k_new))
     _check(rc, "hg_kv_append")
+
+
+def decode_attn_fused(q, k_new, v_new, positions, k_cache, v_cache, out, lse, partial_outs, partial_lses, sm_scale) -> None:
+    ensure_init(q.device)
+    b, nq, hq, d = q.shape
+    assert nq == 1
+    hkv, lk = k_cache.shape[-2], k_cache.shape[1]
+    if positions.dtype == torch.int64:
+        pi64 = 1
+    elif positions.dtype == torch.int32:
+        pi64 = 0
+    else:
+        raise ValueError(f"positions must be int32 or int64, got {positions.dtype}")
+    with torch.cuda.device(q.device):
+        rc = load().hg_decode_attn_fused(
+            _ptr(q), _ptr(k_new), _ptr(v_new), _ptr(positions), pi64, _ptr(k_cache), _ptr(v_cache), _ptr(out), _ptr(lse),
+            b, lk, hq, hkv, d, q.stride(0), q.stride(2), k_cache.stride(0), k_cache.stride(1), k_cache.stride(2),
+            _ptr_table(partial_outs), _ptr_table(partial_lses), len(partial_outs), float(sm_scale), dtype_code(q.dtype), _stream(q))
+    _check(rc, "hg_decode_attn_fused")

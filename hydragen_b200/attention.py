@@ -17,6 +17,7 @@ from torch import Tensor
 
 from . import _lib
 from .flash import (
+    decode_attention_fused,
     flash_attention,
     flash_attention_seqlen,
     flash_attention_varlen,
@@ -31,6 +32,7 @@ __all__ = [
     "combine_lse_torch",
     "hydragen_attention",
     "hydragen_attention_nopad",
+    "hydragen_attention_decode",
     "flash_attention",
     "flash_attention_varlen",
     "flash_attention_seqlen",
@@ -137,6 +139,49 @@ def hydragen_attention(
 
     # suffix branch + (L+1)-way combine in one launch
     out, _ = suffix_attention_fused(q, k, v, seq_lens, causal=seq_lens is None, partial_outs=outs, partial_lses=lses)
+    return out
+
+
+def hydragen_attention_decode(
+    q: Tensor,
+    k_new: Tensor,
+    v_new: Tensor,
+    positions: Tensor,
+    k_cache: Tensor,
+    v_cache: Tensor,
+    shared_ks: List[Tensor],
+    shared_vs: List[Tensor],
+    shared_cu_seq_lens: Optional[List[Optional[Tensor]]] = None,
+    shared_max_seq_lens: Optional[List[Optional[int]]] = None,
+    use_varlens: Optional[List[bool]] = None,
+):
+    """A whole decode step of Hydragen attention for one layer: what the reference's DECODE branch does
+    with ``update_per_completion_kvs`` followed by ``hydragen_attention(..., seq_lens=pos + 1)``
+    (hydragen/llama.py:564-587), in ``len(shared_ks) + 1`` launches: one tcgen05 prefix launch per shared
+    level, then ONE launch that appends the new token's K/V at ``positions[b]``, runs the suffix branch over
+    the sequence's ``positions[b] + 1`` own keys and merges every partial result.  The caches are updated
+    in place; returns ``out [b, 1, hq, d]``."""
+    n = len(shared_ks)
+    shared_cu_seq_lens = shared_cu_seq_lens or [None] * n
+    shared_max_seq_lens = shared_max_seq_lens or [None] * n
+    use_varlens = use_varlens or [False] * n
+    assert q.ndim == 4 and q.shape[1] == 1, f"{q.shape}"
+    assert len(shared_vs) == n and len(shared_cu_seq_lens) == n and len(shared_max_seq_lens) == n and len(use_varlens) == n
+    b = q.shape[0]
+    outs, lses = [], []
+    for sk, sv, scu, smax, use_varlen in zip(shared_ks, shared_vs, shared_cu_seq_lens, shared_max_seq_lens, use_varlens):
+        assert sk.shape == sv.shape, f"{sk.shape} {sv.shape}"
+        if not use_varlen:
+            ng = sk.shape[0]
+            assert b % ng == 0, f"{b} {ng}"
+            so, sl = prefix_attention_grouped(q, sk, sv, n_groups=ng)
+        else:
+            ng = scu.shape[0] - 1
+            assert b % ng == 0, f"{b} {ng}"
+            so, sl = prefix_attention_grouped(q, sk, sv, n_groups=ng, cu_seqlens_k=scu, max_seqlen_k=smax)
+        outs.append(so)
+        lses.append(sl)
+    out, _ = decode_attention_fused(q, k_new, v_new, positions, k_cache, v_cache, outs, lses)
     return out
 
 

@@ -134,6 +134,41 @@ int hg_rowwise_attn_fwd(const void* q, const void* k, const void* v, const void*
   return launch_rowwise(p, dtype, (cudaStream_t)stream);
 }
 
+int hg_decode_attn_fused(const void* q, const void* k_new, const void* v_new, const void* positions, int positions_i64,
+                         void* k_cache, void* v_cache, void* out, float* lse, int b, int lk, int hq, int hkv, int d,
+                         int64_t q_stride_b, int64_t q_stride_h, int64_t kv_stride_b, int64_t kv_stride_s, int64_t kv_stride_h,
+                         const void* const* partial_outs_host, const float* const* partial_lses_host, int n_partials,
+                         float sm_scale, int dtype, void* stream) {
+  if (!valid_dtype(dtype)) return set_error(HG_ERR_INVALID_ARGUMENT, "decode_attn_fused: unknown dtype %d", dtype);
+  if (b < 0 || lk < 1 || hq < 1 || hkv < 1 || d < 1)
+    return set_error(HG_ERR_INVALID_ARGUMENT, "decode_attn_fused: bad sizes b=%d lk=%d hq=%d hkv=%d d=%d", b, lk, hq, hkv, d);
+  if (hq % hkv != 0) return set_error(HG_ERR_INVALID_ARGUMENT, "decode_attn_fused: hq (%d) must be a multiple of hkv (%d)", hq, hkv);
+  if (b > 0 && (!q || !k_new || !v_new || !positions || !k_cache || !v_cache || !out))
+    return set_error(HG_ERR_INVALID_ARGUMENT, "decode_attn_fused: null pointer");
+  const int esz = dtype == HG_F32 ? 4 : 2;
+  const int vec = 16 / esz;
+  if (q_stride_b % vec || q_stride_h % vec || kv_stride_b % vec || kv_stride_s % vec || kv_stride_h % vec ||
+      reinterpret_cast<uintptr_t>(q) % 16 || reinterpret_cast<uintptr_t>(k_new) % 16 || reinterpret_cast<uintptr_t>(v_new) % 16 ||
+      reinterpret_cast<uintptr_t>(k_cache) % 16 || reinterpret_cast<uintptr_t>(v_cache) % 16 || reinterpret_cast<uintptr_t>(out) % 16)
+    return set_error(HG_ERR_UNSUPPORTED, "decode_attn_fused: bases and strides must be 16-byte aligned");
+  RowwiseParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_partials(p.partials, partial_outs_host, partial_lses_host, n_partials, "decode_attn_fused");
+  if (rc != HG_OK) return rc;
+  for (int i = 0; i < n_partials; ++i)
+    if (reinterpret_cast<uintptr_t>(partial_outs_host[i]) % 16)
+      return set_error(HG_ERR_UNSUPPORTED, "decode_attn_fused: partial outs must be 16-byte aligned");
+  p.q = q; p.k = k_cache; p.v = v_cache;
+  p.k_new = k_new; p.v_new = v_new; p.positions = positions; p.positions_i64 = positions_i64;
+  p.kv_group_size = 1;
+  p.out = out; p.lse = lse;
+  p.b = b; p.nq = 1; p.lk = lk; p.hq = hq; p.hkv = hkv; p.d = d;
+  p.q_stride_b = q_stride_b; p.q_stride_s = 0; p.q_stride_h = q_stride_h;
+  p.kv_stride_b = kv_stride_b; p.kv_stride_s = kv_stride_s; p.kv_stride_h = kv_stride_h;
+  p.scale_log2 = sm_scale * kLog2e;
+  return launch_rowwise(p, dtype, (cudaStream_t)stream);
+}
+
 int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int n_groups, int q_per_group,
                        int64_t n_k_rows, int k_len, const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
                        int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype, void* stream) {

@@ -155,6 +155,11 @@ struct RowwiseParams {
   int64_t kv_stride_b, kv_stride_s, kv_stride_h;
   PartialTable partials;
   float scale_log2;  // sm_scale * log2(e)
+  // fused decode step (hg_decode_attn_fused): new token rows [b, hkv, d] appended at positions[b]
+  const void* k_new;
+  const void* v_new;
+  const void* positions;
+  int positions_i64;
 };
 int launch_rowwise(const RowwiseParams& p, int dtype, cudaStream_t s);
 

@@ -290,12 +290,15 @@ __global__ void __launch_bounds__(kRowwiseWarps * 32) rowwise_attn_kernel(const 
 // 16-bit) owns one unit and walks its keys in order, U keys (2U independent 128-bit loads per lane)
 // per trip; the R = Hq/Hkv query rows of the unit share every K/V row.  Adjacent slots are adjacent
 // kv heads of the same cache row, so a warp load covers whole contiguous 256-byte head rows.  No
-// shared memory, no cross-slot merge, 16 units per 256-thread CTA; register use is small enough for
-// >= 24 resident warps per SM, which is what keeps enough bytes in flight for HBM (Little's law:
-// ~31 KB per SM at 6.5 TB/s x 700 ns).  The loop trip count is made warp-uniform (max over the
-// warp's slots) so the LPK-lane shuffles never diverge; out-of-range keys are predicated off and
-// never read (xformers_stuff.py:274-279).
-template <typename T, int D, int R, int U, int MINB>
+// shared memory, no cross-slot merge, 16 units per 256-thread CTA.  Full U-key trips run without
+// predicates; the ragged tail is one more trip whose key slots are skipped warp-uniformly, so a
+// sequence with a single key executes a single key's worth of instructions.
+//
+// kFused: the step's KV append (hydragen/llama.py:250-257) happens here as well.  The new token's
+// K/V row is read once from k_new / v_new, stored to row positions[b] of the caches and attended to
+// from registers as the last key (len_b = positions[b] + 1); the cache is only read for the
+// len_b - 1 older keys.  One launch then replaces scatter_ x2 + cast + split-K + reduce + combine.
+template <typename T, int D, int R, int U, int MINB, bool kFused>
 __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwiseParams p) {
   constexpr int VEC = Vec16<T>::VEC;
   constexpr int LPK = D / VEC;
@@ -309,23 +312,38 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
   const int b_idx = valid ? (int)(unit / p.hkv) : 0;
   const int kvh = valid ? (int)(unit % p.hkv) : 0;
 
+  // keys read from the cache: [0, len); fused: the new token sits at row `len` and is not re-read
   int len = 0;
   if (valid) {
-    len = p.lk;
-    if (p.seq_lens != nullptr) {
-      const int64_t sl = p.seq_lens_i64 ? __ldg(reinterpret_cast<const int64_t*>(p.seq_lens) + b_idx)
-                                        : (int64_t)__ldg(reinterpret_cast<const int32_t*>(p.seq_lens) + b_idx);
-      len = (int)max((int64_t)0, min((int64_t)len, sl));
+    if constexpr (kFused) {
+      const int64_t pos = p.positions_i64 ? __ldg(reinterpret_cast<const int64_t*>(p.positions) + b_idx)
+                                          : (int64_t)__ldg(reinterpret_cast<const int32_t*>(p.positions) + b_idx);
+      len = (int)max((int64_t)0, min((int64_t)p.lk - 1, pos));
+    } else {
+      len = p.lk;
+      if (p.seq_lens != nullptr) {
+        const int64_t sl = p.seq_lens_i64 ? __ldg(reinterpret_cast<const int64_t*>(p.seq_lens) + b_idx)
+                                          : (int64_t)__ldg(reinterpret_cast<const int32_t*>(p.seq_lens) + b_idx);
+        len = (int)max((int64_t)0, min((int64_t)len, sl));
+      }
     }
   }
   // first output row of the unit: rows (b, 0, kvh*R + r), r < R, are contiguous
   const int64_t orow0 = (int64_t)b_idx * p.hq + (int64_t)kvh * R;
   const int np = p.partials.n;
 
-  // independent of len: the query rows and the first prefix partial (the common decode case is one
-  // shared level) are requested before the key loop so their latency overlaps it
+  // independent of len: the query rows, the new K/V row and the first prefix partial (the common
+  // decode case is one shared level) are requested before the key loop so their latency overlaps it
   uint4 qraw[R], p0raw[R];
   float p0lse[R];
+  uint4 knew = make_uint4(0, 0, 0, 0), vnew = make_uint4(0, 0, 0, 0);
+  if constexpr (kFused) {
+    if (valid) {
+      const int64_t o = ((int64_t)b_idx * p.hkv + kvh) * D + dl * VEC;
+      knew = ld_stream_v4(reinterpret_cast<const T*>(p.k_new) + o);
+      vnew = ld_stream_v4(reinterpret_cast<const T*>(p.v_new) + o);
+    }
+  }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     qraw[r] = make_uint4(0, 0, 0, 0);
@@ -339,12 +357,23 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
       }
     }
   }
-  int len_max = len;
+  int len_max = len, len_min = valid ? len : 0x7fffffff;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) len_max = max(len_max, __shfl_xor_sync(0xffffffffu, len_max, o));
+  for (int o = 16; o > 0; o >>= 1) {
+    len_max = max(len_max, __shfl_xor_sync(0xffffffffu, len_max, o));
+    len_min = min(len_min, __shfl_xor_sync(0xffffffffu, len_min, o));
+  }
+  len_min = min(len_min, len_max);  // a warp with no valid slot: 0
 
-  const T* kb = reinterpret_cast<const T*>(p.k) + (int64_t)b_idx * p.kv_stride_b + (int64_t)kvh * p.kv_stride_h + dl * VEC;
-  const T* vb = reinterpret_cast<const T*>(p.v) + (int64_t)b_idx * p.kv_stride_b + (int64_t)kvh * p.kv_stride_h + dl * VEC;
+  const int64_t kv_off = (int64_t)b_idx * p.kv_stride_b + (int64_t)kvh * p.kv_stride_h + dl * VEC;
+  const T* kb = reinterpret_cast<const T*>(p.k) + kv_off;
+  const T* vb = reinterpret_cast<const T*>(p.v) + kv_off;
+  if constexpr (kFused) {
+    if (valid) {  // the append: row `len` of this sequence's caches
+      st_v4(const_cast<T*>(kb) + (int64_t)len * p.kv_stride_s, knew);
+      st_v4(const_cast<T*>(vb) + (int64_t)len * p.kv_stride_s, vnew);
+    }
+  }
 
   float qf[R][VEC];
   RowState<VEC> st[R];
@@ -359,12 +388,38 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
     for (int e = 0; e < VEC; ++e) st[r].acc[e] = 0.f;
   }
 
-  for (int j0 = 0; j0 < len_max; j0 += U) {
+  // one key (already in registers) into the running state of every query row of the unit
+  auto absorb = [&](const uint4& kraw, const uint4& vraw, bool live) {
+    float kf[VEC], vf[VEC];
+    Vec16<T>::unpack(kraw, kf);
+    Vec16<T>::unpack(vraw, vf);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) d = fmaf(qf[r][e], kf[e], d);
+#pragma unroll
+      for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      const float sc = live ? d : -INFINITY;
+      const float m_new = fmaxf(st[r].m, sc);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = fast_exp2(st[r].m - m_safe);
+      const float pw = fast_exp2(sc - m_safe);
+      st[r].l = st[r].l * alpha + pw;
+      st[r].m = m_new;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) st[r].acc[e] = fmaf(pw, vf[e], st[r].acc[e] * alpha);
+    }
+  };
+
+  // ---- full trips: U keys, no predicates -------------------------------------------------------
+  int j0 = 0;
+  for (; j0 + U <= len_min; j0 += U) {
     uint4 kraw[U], vraw[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) kraw[u] = (j0 + u < len) ? ld_stream_v4(kb + (int64_t)(j0 + u) * p.kv_stride_s) : make_uint4(0, 0, 0, 0);
+    for (int u = 0; u < U; ++u) kraw[u] = ld_stream_v4(kb + (int64_t)(j0 + u) * p.kv_stride_s);
 #pragma unroll
-    for (int u = 0; u < U; ++u) vraw[u] = (j0 + u < len) ? ld_stream_v4(vb + (int64_t)(j0 + u) * p.kv_stride_s) : make_uint4(0, 0, 0, 0);
+    for (int u = 0; u < U; ++u) vraw[u] = ld_stream_v4(vb + (int64_t)(j0 + u) * p.kv_stride_s);
     float s[U][R];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -377,7 +432,7 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
         for (int e = 0; e < VEC; ++e) d = fmaf(qf[r][e], kf[e], d);
 #pragma unroll
         for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        s[u][r] = (j0 + u < len) ? d : -INFINITY;
+        s[u][r] = d;
       }
     }
 #pragma unroll
@@ -385,13 +440,12 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
       float m_new = st[r].m;
 #pragma unroll
       for (int u = 0; u < U; ++u) m_new = fmaxf(m_new, s[u][r]);
-      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = fast_exp2(st[r].m - m_safe);
+      const float alpha = fast_exp2(st[r].m - m_new);  // scores are finite here: m_new > -inf
       float pu[U];
       float psum = 0.f;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        pu[u] = fast_exp2(s[u][r] - m_safe);
+        pu[u] = fast_exp2(s[u][r] - m_new);
         psum += pu[u];
       }
       st[r].l = st[r].l * alpha + psum;
@@ -407,6 +461,23 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
       }
     }
   }
+  // ---- ragged tail: fewer than U keys for some slot; all loads first, then key by key ------------
+  for (; j0 < len_max; j0 += U) {
+    uint4 kraw[U], vraw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      kraw[u] = make_uint4(0, 0, 0, 0);
+      vraw[u] = make_uint4(0, 0, 0, 0);
+      if (j0 + u < len) {
+        kraw[u] = ld_stream_v4(kb + (int64_t)(j0 + u) * p.kv_stride_s);
+        vraw[u] = ld_stream_v4(vb + (int64_t)(j0 + u) * p.kv_stride_s);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (j0 + u < len_max) absorb(kraw[u], vraw[u], j0 + u < len);  // warp-uniform skip
+  }
+  if constexpr (kFused) absorb(knew, vnew, valid);
 
   if (!valid) return;
 #pragma unroll
@@ -419,34 +490,29 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
 #pragma unroll
     for (int e = 0; e < VEC; ++e) o[e] = st[r].acc[e] * inv_l;
     if (np > 0) {
-      float pl[HG_MAX_COMBINE];
-      uint4 praw[HG_MAX_COMBINE];
-      pl[0] = p0lse[r];
-      praw[0] = p0raw[r];
-      float mx = fmaxf(lse, pl[0]);
-#pragma unroll
-      for (int i = 1; i < HG_MAX_COMBINE; ++i) {
-        if (i < np) {
-          pl[i] = __ldg(p.partials.lses[i] + orow);
-          praw[i] = ld_stream_v4(reinterpret_cast<const T*>(p.partials.outs[i]) + orow * D + dl * VEC);
-          mx = fmaxf(mx, pl[i]);
-        }
-      }
+      // merge with the prefix partials: first one prefetched, further shared levels one by one
+      float mx = fmaxf(lse, p0lse[r]);
+      for (int i = 1; i < np; ++i) mx = fmaxf(mx, __ldg(p.partials.lses[i] + orow));
       const float mx_safe = (mx == -INFINITY) ? 0.f : mx;
       const float w_s = __expf(lse - mx_safe);
       float den = w_s;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) o[e] *= w_s;
+      {
+        const float w = __expf(p0lse[r] - mx_safe);
+        den += w;
+        float f[VEC];
+        Vec16<T>::unpack(p0raw[r], f);
 #pragma unroll
-      for (int i = 0; i < HG_MAX_COMBINE; ++i) {
-        if (i < np) {
-          const float w = __expf(pl[i] - mx_safe);
-          den += w;
-          float f[VEC];
-          Vec16<T>::unpack(praw[i], f);
+        for (int e = 0; e < VEC; ++e) o[e] = fmaf(w, f[e], o[e]);
+      }
+      for (int i = 1; i < np; ++i) {
+        const float w = __expf(__ldg(p.partials.lses[i] + orow) - mx_safe);
+        den += w;
+        float f[VEC];
+        Vec16<T>::unpack(ld_stream_v4(reinterpret_cast<const T*>(p.partials.outs[i]) + orow * D + dl * VEC), f);
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) o[e] = fmaf(w, f[e], o[e]);
-        }
+        for (int e = 0; e < VEC; ++e) o[e] = fmaf(w, f[e], o[e]);
       }
       const float inv = den > 0.f ? 1.f / den : 0.f;
 #pragma unroll
@@ -462,13 +528,14 @@ template <typename T, int D, int R>
 static int launch_decode_slot(const RowwiseParams& p, cudaStream_t s) {
   constexpr int VEC = Vec16<T>::VEC;
   constexpr int SLOTS = 256 / (D / VEC);
+  constexpr int MINB = (R == 1 ? 3 : (R <= 4 ? 2 : 1));
   const int64_t n_units = (int64_t)p.b * p.hkv;
   const int64_t blocks = (n_units + SLOTS - 1) / SLOTS;
   if (blocks > 0x7fffffffLL) return set_error(HG_ERR_UNSUPPORTED, "rowwise: too many units (%lld)", (long long)n_units);
-  if (p.lk <= 8)  // a handful of keys: fewer registers -> more resident warps to hide the dependent-load chain
-    decode_slot_kernel<T, D, R, 2, (R == 1 ? 4 : (R <= 4 ? 2 : 1))><<<(unsigned)blocks, 256, 0, s>>>(p);
+  if (p.k_new != nullptr)
+    decode_slot_kernel<T, D, R, 4, MINB, true><<<(unsigned)blocks, 256, 0, s>>>(p);
   else
-    decode_slot_kernel<T, D, R, 4, (R == 1 ? 3 : (R <= 4 ? 2 : 1))><<<(unsigned)blocks, 256, 0, s>>>(p);
+    decode_slot_kernel<T, D, R, 4, MINB, false><<<(unsigned)blocks, 256, 0, s>>>(p);
   return check_launch("decode_slot_attn");
 }
 
@@ -487,7 +554,10 @@ static int launch_rowwise_d(const RowwiseParams& p, cudaStream_t s) {
   const int M = p.nq * (p.hq / p.hkv);
   // decode shape with enough independent units (or few keys): the slot kernel
   const int64_t n_units = (int64_t)p.b * p.hkv;
-  if (p.nq == 1 && p.cu_seqlens_k == nullptr && p.kv_group_size == 1 && (n_units >= 2048 || p.lk <= 64)) {
+  const bool fused = p.k_new != nullptr;
+  if (fused && !(p.nq == 1 && p.cu_seqlens_k == nullptr && p.kv_group_size == 1 && (M == 1 || M == 2 || M == 4 || M == 8)))
+    return set_error(HG_ERR_UNSUPPORTED, "decode_attn_fused: needs nq == 1 and hq/hkv in {1, 2, 4, 8}");
+  if (p.nq == 1 && p.cu_seqlens_k == nullptr && p.kv_group_size == 1 && (fused || n_units >= 2048 || p.lk <= 64)) {
     switch (M) {
       case 1: return launch_decode_slot<T, D, 1>(p, s);
       case 2: return launch_decode_slot<T, D, 2>(p, s);

@@ -210,3 +210,30 @@ def suffix_attention_fused(q, k, v, seq_len, causal, partial_outs, partial_lses)
     """Suffix branch + combine in one launch (hydragen/attention.py:343-352): the per-sequence
     result is merged in registers with the prefix partials; returns (final out, merged lse)."""
     return _rowwise(q, k, v, seq_len, causal, partial_outs, partial_lses)
+
+
+def decode_attention_fused(q: Tensor, k_new: Tensor, v_new: Tensor, positions: Tensor, k_cache: Tensor, v_cache: Tensor,
+                           partial_outs=(), partial_lses=()) -> Tuple[Tensor, Tensor]:
+    """One decode step of the suffix side in one launch: append ``k_new / v_new`` ``[b, 1, hkv, d]`` at row
+    ``positions[b]`` of the unique caches ``[b_max, lk, hkv, d]``, attend ``q [b, 1, hq, d]`` to the
+    ``positions[b] + 1`` keys of its own sequence and merge with the prefix partials.  Replaces
+    ``update_per_completion_kvs`` + ``flash_attention_seqlen`` + ``combine_lse`` of the reference's decode
+    branch (hydragen/llama.py:565-587).  Returns (out, merged lse [b, 1, hq])."""
+    _check_qkv(q, k_new, v_new)
+    b, nq, hq, d = q.shape
+    if nq != 1 or k_new.shape[1] != 1:
+        raise ValueError("decode_attention_fused takes exactly one new token per sequence")
+    if k_cache.shape != v_cache.shape or k_cache.stride() != v_cache.stride() or k_cache.stride(-1) != 1:
+        raise ValueError("k_cache / v_cache must share shape and strides, head_dim contiguous")
+    if k_cache.shape[0] < b or k_cache.shape[2:] != k_new.shape[2:] or k_cache.dtype != q.dtype:
+        raise ValueError(f"cache {tuple(k_cache.shape)} does not match new rows {tuple(k_new.shape)}")
+    if not _inner_ok(q):
+        q = q.contiguous()
+    positions = positions.reshape(-1)
+    if positions.shape[0] != b:
+        raise ValueError("positions must hold one row index per sequence")
+    out = torch.empty((b, 1, hq, d), device=q.device, dtype=q.dtype)
+    lse = torch.empty((b, 1, hq), device=q.device, dtype=torch.float32)
+    _lib.decode_attn_fused(q, k_new.contiguous(), v_new.contiguous(), positions.contiguous(), k_cache, v_cache, out, lse,
+                           list(partial_outs), list(partial_lses), d**-0.5)
+    return out, lse

@@ -37,7 +37,7 @@ import torch
 from torch import Tensor, nn
 
 from . import _lib
-from .attention import hydragen_attention
+from .attention import hydragen_attention, hydragen_attention_decode
 from .flash import flash_attention, flash_attention_seqlen
 
 kv_append = _lib.kv_append  # (k_new, v_new, positions, k_cache, v_cache): module-level so tests can swap it
@@ -327,6 +327,12 @@ def hydragen_attention_on_caches(q: Tensor, k: Tensor, v: Tensor, shared_caches:
     """Adapts cache objects to the operator's argument lists (hydragen/llama.py:355-414): uniform
     levels are passed as [sb, L, Hkv, d] views of the packed buffer, ragged levels as the packed
     buffer + cumsum_lengths + max length."""
+    keys, values, cu, mx, uv = _shared_cache_args(shared_caches)
+    return hydragen_attention(q, k, v, shared_ks=keys, shared_vs=values, shared_cu_seq_lens=cu, shared_max_seq_lens=mx,
+                              use_varlens=uv, seq_lens=seq_len)
+
+
+def _shared_cache_args(shared_caches: List["SharedCache"]):
     keys, values, cu, mx, uv = [], [], [], [], []
     for sc in shared_caches:
         if sc.use_varlen:
@@ -341,8 +347,18 @@ def hydragen_attention_on_caches(q: Tensor, k: Tensor, v: Tensor, shared_caches:
             cu.append(None)
             mx.append(None)
         uv.append(sc.use_varlen)
-    return hydragen_attention(q, k, v, shared_ks=keys, shared_vs=values, shared_cu_seq_lens=cu, shared_max_seq_lens=mx,
-                              use_varlens=uv, seq_lens=seq_len)
+    return keys, values, cu, mx, uv
+
+
+def hydragen_decode_on_caches(q: Tensor, k_new: Tensor, v_new: Tensor, positions: Tensor, cache: "PerLayerKVCache",
+                              shared_caches: List["SharedCache"]):
+    """The DECODE branch of the reference (hydragen/llama.py:564-587: update_per_completion_kvs, then
+    hydragen_attention_on_caches / flash_attention_seqlen with seq_len = position + 1) as one prefix launch
+    per shared level + ONE fused launch (append + suffix + combine)."""
+    keys, values, cu, mx, uv = _shared_cache_args(shared_caches)
+    bs = q.shape[0]
+    return hydragen_attention_decode(q, k_new, v_new, positions, cache.per_completion_k_cache[:bs], cache.per_completion_v_cache[:bs],
+                                     keys, values, cu, mx, uv)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -374,6 +390,7 @@ class HydragenLlamaAttention(nn.Module):
         self.num_key_value_groups = self.num_heads // self.num_key_value_heads
         self.disable_hydragen = False
         self.disable_attention = False  # throughput upper-bound ablation (hydragen/llama.py:433-437)
+        self.fused_decode = True  # decode steps use the fused append + suffix + combine launch
         bias = bool(getattr(config, "attention_bias", False))
         self.q_proj = nn.Linear(self.hidden_size, self.num_heads * self.head_dim, bias=bias)
         self.k_proj = nn.Linear(self.hidden_size, self.num_key_value_heads * self.head_dim, bias=bias)
@@ -412,11 +429,16 @@ class HydragenLlamaAttention(nn.Module):
                     out = hydragen_attention_on_caches(q, k, v, cache.get_used_shared_caches())
                 cache.update_per_completion_kvs(ctx.unique_position_ids, k, v)
         elif self.mode == AttentionMode.DECODE:
-            kc, vc = cache.update_per_completion_kvs(ctx.unique_position_ids, k, v)
-            if not cache.has_shared() or self.disable_hydragen:
-                out, _ = flash_attention_seqlen(q, kc, vc, seq_len=ctx.seq_lens)
-            else:
-                out = hydragen_attention_on_caches(q, kc, vc, cache.get_used_shared_caches(), seq_len=ctx.seq_lens)  # THE HOT PATH
+            if self.fused_decode and s == 1 and self.num_key_value_groups in (1, 2, 4, 8):
+                # THE HOT PATH: prefix launch(es) + one launch for append + suffix + combine
+                shared = [] if (self.disable_hydragen or not cache.has_shared()) else cache.get_used_shared_caches()
+                out = hydragen_decode_on_caches(q, k, v, ctx.unique_position_ids, cache, shared)
+            else:  # the reference's call sequence, primitive by primitive (hydragen/llama.py:564-587)
+                kc, vc = cache.update_per_completion_kvs(ctx.unique_position_ids, k, v)
+                if not cache.has_shared() or self.disable_hydragen:
+                    out, _ = flash_attention_seqlen(q, kc, vc, seq_len=ctx.seq_lens)
+                else:
+                    out = hydragen_attention_on_caches(q, kc, vc, cache.get_used_shared_caches(), seq_len=ctx.seq_lens)
         else:
             raise ValueError(f"Unknown mode {self.mode}")
 

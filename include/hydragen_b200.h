@@ -150,6 +150,29 @@ int hg_kv_append(const void* k_new, const void* v_new, const void* positions, in
                  void* k_cache, void* v_cache, int b, int nq, int lk, int hkv, int d, int dtype,
                  void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * One decode step of the suffix side in ONE launch: KV append + suffix attention + combine.
+ * Replaces, for nq == 1 (every decode step: hydragen/llama.py:564-587),
+ *   - PerLayerKVCache.update_per_completion_kvs (llama.py:236-262: two scatter_ calls),
+ *   - flash_attention_seqlen (hydragen/flash.py:163-281: cast + split-K kernel + reduce kernel),
+ *   - combine_lse (hydragen/attention.py:352),
+ * with seq_len[b] = positions[b] + 1 (llama.py:569) computed in the kernel.  The new token's K/V
+ * row is written to row positions[b] of the caches and attended to from registers; only the
+ * positions[b] older rows of the cache are read.
+ *   q            [b, 1, hq, d]   strides q_stride_b, q_stride_h (elements)
+ *   k_new, v_new [b, 1, hkv, d]  contiguous
+ *   positions    [b] int32 / int64, 0 <= positions[b] < lk
+ *   k_cache, v_cache [b_max, lk, hkv, d] with strides kv_stride_b/s/h (written at row positions[b])
+ *   out [b, 1, hq, d] contiguous; lse [b, 1, hq] fp32 or NULL; partial_* as in hg_rowwise_attn_fwd.
+ * hq / hkv must be 1, 2, 4 or 8; d as for hg_rowwise_attn_fwd.
+ */
+int hg_decode_attn_fused(const void* q, const void* k_new, const void* v_new, const void* positions,
+                         int positions_i64, void* k_cache, void* v_cache, void* out, float* lse, int b,
+                         int lk, int hq, int hkv, int d, int64_t q_stride_b, int64_t q_stride_h,
+                         int64_t kv_stride_b, int64_t kv_stride_s, int64_t kv_stride_h,
+                         const void* const* partial_outs_host, const float* const* partial_lses_host,
+                         int n_partials, float sm_scale, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

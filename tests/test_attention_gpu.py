@@ -300,3 +300,64 @@ def test_kv_append():
     rk[:b].scatter_(1, idx, kn)
     rv[:b].scatter_(1, idx, vn)
     assert torch.equal(kc, rk) and torch.equal(vc, rv)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("cfg", [(37, 8, 8, 128, 48), (64, 8, 1, 128, 16), (5, 4, 2, 64, 33), (130, 32, 32, 128, 16), (3, 16, 4, 128, 200)])
+def test_decode_attention_fused(dtype, cfg):
+    """KV append + suffix attention in one launch (no prefix partials): cache rows written exactly where
+    the reference's scatter_ puts them (hydragen/llama.py:250-257), output == flash_attention_seqlen with
+    seq_len = position + 1 (llama.py:569) on the updated cache."""
+    from hydragen_b200.flash import decode_attention_fused
+
+    b, hq, hkv, d, lk = cfg
+    g = torch.Generator().manual_seed(b * 7 + hq + lk)
+    q = torch.randn(b, 1, hq, d, generator=g).to(dtype)
+    kn = torch.randn(b, 1, hkv, d, generator=g).to(dtype)
+    vn = torch.randn(b, 1, hkv, d, generator=g).to(dtype)
+    kc = torch.randn(b + 1, lk, hkv, d, generator=g).to(dtype)
+    vc = torch.randn(b + 1, lk, hkv, d, generator=g).to(dtype)
+    pos = torch.randint(0, lk, (b, 1), generator=g)
+    pos[0, 0], pos[-1, 0] = 0, lk - 1  # first and last row of the cache
+    kcd, vcd = kc.cuda(), vc.cuda()
+    out, lse = decode_attention_fused(q.cuda(), kn.cuda(), vn.cuda(), pos.cuda(), kcd[:b], vcd[:b])
+    torch.cuda.synchronize()
+    rk, rv = kc.clone(), vc.clone()
+    idx = pos.view(b, 1, 1, 1).expand(b, 1, hkv, d)
+    rk[:b].scatter_(1, idx, kn)
+    rv[:b].scatter_(1, idx, vn)
+    assert torch.equal(kcd.cpu(), rk) and torch.equal(vcd.cpu(), rv)  # append is a bit-exact copy; nothing else touched
+    ro, rl = O.flash_attention_seqlen(q, rk[:b], rv[:b], seq_len=pos[:, 0] + 1)
+    _assert_close(out, ro, dtype, "out")
+    assert (lse.double().cpu() - rl).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("sizes", [[[1], [96]], [[2], [5, 5]], [[3, 3], [7, 9, 11, 4, 6, 2]]])
+def test_hydragen_attention_decode_matches_unfused(sizes):
+    """hydragen_attention_decode (prefix + fused append/suffix/combine) == kv_append followed by
+    hydragen_attention(seq_lens = pos + 1), and both match the oracle on the updated cache."""
+    from hydragen_b200 import _lib
+    from hydragen_b200.attention import hydragen_attention, hydragen_attention_decode
+
+    hq, hkv, d, dtype = 8, 2, 128, torch.bfloat16
+    c = O.build_case(sizes, hq, hkv, d, dtype=dtype, seed=3)
+    b = c["q"].shape[0]
+    g = torch.Generator().manual_seed(17)
+    lk = c["k"].shape[1] + 3
+    kc = torch.randn(b, lk, hkv, d, generator=g).to(dtype)
+    vc = torch.randn(b, lk, hkv, d, generator=g).to(dtype)
+    kn = torch.randn(b, 1, hkv, d, generator=g).to(dtype)
+    vn = torch.randn(b, 1, hkv, d, generator=g).to(dtype)
+    pos = torch.randint(0, lk, (b, 1), generator=g)
+    shared = {k: _dev(c[k]) for k in ("shared_ks", "shared_vs", "shared_cu_seq_lens", "shared_max_seq_lens", "use_varlens")}
+    k1, v1 = kc.cuda(), vc.cuda()
+    out1 = hydragen_attention_decode(c["q"].cuda(), kn.cuda(), vn.cuda(), pos.cuda(), k1, v1, **shared)
+    k2, v2 = kc.cuda(), vc.cuda()
+    _lib.kv_append(kn.cuda(), vn.cuda(), pos.cuda(), k2, v2)
+    out2 = hydragen_attention(c["q"].cuda(), k2, v2, seq_lens=(pos[:, 0] + 1).cuda(), **shared)
+    torch.cuda.synchronize()
+    assert torch.equal(k1, k2) and torch.equal(v1, v2)
+    _assert_close(out1, out2, dtype, "fused vs unfused")
+    ref = O.hydragen_attention(c["q"], k2.cpu(), v2.cpu(), c["shared_ks"], c["shared_vs"], c["shared_cu_seq_lens"], c["shared_max_seq_lens"],
+                               c["use_varlens"], seq_lens=pos[:, 0] + 1)
+    _assert_close(out1, ref, dtype, "fused vs oracle")
