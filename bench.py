@@ -196,6 +196,11 @@ class ClockSampler:
         return out
 
 
+def _log(msg):
+    if os.environ.get("HG_BENCH_VERBOSE"):
+        print(f"[bench r{os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -249,9 +254,11 @@ def run_ours(a):
 
     launches_per_step = L * 2  # prefix + fused append/suffix/combine (NCCL kernels not counted)
 
+    _log("inputs ready; eager warm-up")
     for _ in range(3):
         step_eager()
     torch.cuda.synchronize()
+    _log("eager warm-up done; capturing")
     graph = None
     if not a.no_graph:
         try:
@@ -269,6 +276,7 @@ def run_ours(a):
             if rank == 0:
                 print(f"[bench] CUDA graph capture failed ({ex!r}); timing eager launches", file=sys.stderr)
     step = graph.replay if graph is not None else step_eager
+    _log(f"capture done (graph={graph is not None})")
 
     def barrier():
         if world > 1:
@@ -287,6 +295,7 @@ def run_ours(a):
     e1.record()
     barrier()
     t_ms = e0.elapsed_time(e1)
+    _log(f"timed region done: {t_ms / a.steps:.3f} ms/step")
     clocks = sampler.stop() if sampler is not None else None
     if world > 1:
         tt = torch.tensor([t_ms], device=dev, dtype=torch.float64)
@@ -336,6 +345,7 @@ def run_ours(a):
 
     pre_t = time_kernel_graph(only_prefix)
     suf_t = time_kernel_graph(only_suffix)
+    _log(f"per-kernel timing done: prefix {pre_t:.1f} us, suffix {suf_t:.1f} us")
     pre_flops = 4.0 * B * H * a.prefix_len * D
     esz = 2
     # new K,V rows read + appended, older K,V rows read, q + prefix partial + out, 2 LSE rows
@@ -410,7 +420,16 @@ def run_ours(a):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # NCCL teardown can block while captured graphs still hold its kernels: drop them first, and never let
+        # a stuck teardown outlive the printed result
+        import threading
+
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        del step, graph
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():

@@ -41,6 +41,12 @@ SYMBOLS = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
          c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_void_p],
     ),
+    "hg_prefix_attn_split_fwd": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
+         c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_int, c_void_p],
+    ),
+    "hg_prefix_suggest_splits": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "hg_decode_attn_fused": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -164,14 +170,26 @@ def rowwise_attn_fwd(q, k, v, seq_lens, cu_seqlens_k, kv_group_size, causal, out
 
 
 def prefix_attn_fwd(q, k, v, out, lse, n_groups, q_per_group, n_k_rows, k_len, cu_seqlens_k, max_k_len,
-                    hq, hkv, d, q_stride_row, kv_stride_row, sm_scale) -> None:
+                    hq, hkv, d, q_stride_row, kv_stride_row, sm_scale, kv_splits: int = 1) -> None:
+    """out / lse hold kv_splits partial results back to back ([kv_splits, rows, hq, d] / [kv_splits, rows, hq])."""
     ensure_init(q.device)
     with torch.cuda.device(q.device):
-        rc = load().hg_prefix_attn_fwd(
-            _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), n_groups, q_per_group, n_k_rows, k_len,
-            _ptr(cu_seqlens_k), max_k_len, hq, hkv, d, q_stride_row, kv_stride_row, float(sm_scale),
-            dtype_code(q.dtype), _stream(q))
+        if kv_splits == 1:
+            rc = load().hg_prefix_attn_fwd(
+                _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), n_groups, q_per_group, n_k_rows, k_len,
+                _ptr(cu_seqlens_k), max_k_len, hq, hkv, d, q_stride_row, kv_stride_row, float(sm_scale),
+                dtype_code(q.dtype), _stream(q))
+        else:
+            rc = load().hg_prefix_attn_split_fwd(
+                _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), n_groups, q_per_group, n_k_rows, k_len,
+                _ptr(cu_seqlens_k), max_k_len, hq, hkv, d, q_stride_row, kv_stride_row, float(sm_scale),
+                dtype_code(q.dtype), kv_splits, _stream(q))
     _check(rc, "hg_prefix_attn_fwd")
+
+
+def prefix_suggest_splits(device, n_groups: int, q_per_group: int, hq: int, max_k_len: int, max_splits: int) -> int:
+    ensure_init(device)
+    return int(load().hg_prefix_suggest_splits(n_groups, q_per_group, hq, max_k_len, max_splits))
 
 
 def kv_append(k_new, v_new, positions, k_cache, v_cache) -> None:

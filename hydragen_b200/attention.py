@@ -22,6 +22,7 @@ from .flash import (
     flash_attention_seqlen,
     flash_attention_varlen,
     prefix_attention_grouped,
+    prefix_attention_partials,
     suffix_attention_fused,
 )
 
@@ -118,19 +119,21 @@ def hydragen_attention(
 
     b, nq, hq, d = q.shape
     outs, lses = [], []
+    early = k.shape[1] == 0 and len(shared_ks) == 1
+    max_splits = 1 if early else max(1, _lib.HG_MAX_COMBINE // max(1, len(shared_ks)))
     for sk, sv, scu, smax, use_varlen in zip(shared_ks, shared_vs, shared_cu_seq_lens, shared_max_seq_lens, use_varlens):
         if not use_varlen:
             n = sk.shape[0]
             assert b % n == 0, f"{b} {n}"
-            so, sl = prefix_attention_grouped(q, sk, sv, n_groups=n)
+            so, sl = prefix_attention_partials(q, sk, sv, n_groups=n, max_splits=max_splits)
         else:
             n = scu.shape[0] - 1
             assert b % n == 0, f"{b} {n}"
-            so, sl = prefix_attention_grouped(q, sk, sv, n_groups=n, cu_seqlens_k=scu, max_seqlen_k=smax)
-        if k.shape[1] == 0 and len(shared_ks) == 1:
-            return so  # attention.py:273-274, 330-331
-        outs.append(so)
-        lses.append(sl)
+            so, sl = prefix_attention_partials(q, sk, sv, n_groups=n, cu_seqlens_k=scu, max_seqlen_k=smax, max_splits=max_splits)
+        if early:
+            return so[0]  # attention.py:273-274, 330-331
+        outs += so
+        lses += sl
 
     if k.shape[1] == 0:
         # >= 2 shared levels and no unique keys: undefined in the reference (flash-attn with
@@ -169,18 +172,19 @@ def hydragen_attention_decode(
     assert len(shared_vs) == n and len(shared_cu_seq_lens) == n and len(shared_max_seq_lens) == n and len(use_varlens) == n
     b = q.shape[0]
     outs, lses = [], []
+    max_splits = max(1, _lib.HG_MAX_COMBINE // max(1, n))
     for sk, sv, scu, smax, use_varlen in zip(shared_ks, shared_vs, shared_cu_seq_lens, shared_max_seq_lens, use_varlens):
         assert sk.shape == sv.shape, f"{sk.shape} {sv.shape}"
         if not use_varlen:
             ng = sk.shape[0]
             assert b % ng == 0, f"{b} {ng}"
-            so, sl = prefix_attention_grouped(q, sk, sv, n_groups=ng)
+            so, sl = prefix_attention_partials(q, sk, sv, n_groups=ng, max_splits=max_splits)
         else:
             ng = scu.shape[0] - 1
             assert b % ng == 0, f"{b} {ng}"
-            so, sl = prefix_attention_grouped(q, sk, sv, n_groups=ng, cu_seqlens_k=scu, max_seqlen_k=smax)
-        outs.append(so)
-        lses.append(sl)
+            so, sl = prefix_attention_partials(q, sk, sv, n_groups=ng, cu_seqlens_k=scu, max_seqlen_k=smax, max_splits=max_splits)
+        outs += so
+        lses += sl
     out, _ = decode_attention_fused(q, k_new, v_new, positions, k_cache, v_cache, outs, lses)
     return out
 

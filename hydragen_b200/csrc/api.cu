@@ -172,6 +172,20 @@ int hg_decode_attn_fused(const void* q, const void* k_new, const void* v_new, co
 int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int n_groups, int q_per_group,
                        int64_t n_k_rows, int k_len, const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
                        int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype, void* stream) {
+  return hg_prefix_attn_split_fwd(q, k, v, out, lse, n_groups, q_per_group, n_k_rows, k_len, cu_seqlens_k, max_k_len, hq, hkv, d,
+                                  q_stride_row, kv_stride_row, sm_scale, dtype, 1, stream);
+}
+
+int hg_prefix_suggest_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits) {
+  if (n_groups < 1 || q_per_group < 1 || hq < 1 || max_k_len < 1 || max_splits < 1) return 1;
+  return suggest_prefix_splits(n_groups, q_per_group, hq, max_k_len, max_splits > HG_MAX_COMBINE ? HG_MAX_COMBINE : max_splits);
+}
+
+int hg_prefix_attn_split_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int n_groups, int q_per_group,
+                             int64_t n_k_rows, int k_len, const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
+                             int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype, int kv_splits, void* stream) {
+  if (kv_splits < 1 || kv_splits > HG_MAX_COMBINE)
+    return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: kv_splits = %d outside [1, %d]", kv_splits, HG_MAX_COMBINE);
   if (!g_info.ready) return set_error(HG_ERR_NOT_INITIALIZED, "prefix: hg_init() has not been called");
   if (n_groups < 0 || q_per_group < 0 || n_k_rows < 0 || hq < 1 || hkv < 1)
     return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: bad sizes n_groups=%d q_per_group=%d n_k_rows=%lld hq=%d hkv=%d", n_groups,
@@ -182,7 +196,7 @@ int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, f
                      (long long)n_k_rows);
   if (n_groups > 0 && q_per_group > 0 && (q == nullptr || out == nullptr || k == nullptr || v == nullptr))
     return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: null tensor pointer");
-  if ((int64_t)n_groups * q_per_group > 0x7fffffffLL || n_k_rows > 0x7fffffffLL)
+  if ((int64_t)n_groups * q_per_group * kv_splits > 0x7fffffffLL || n_k_rows > 0x7fffffffLL)
     return set_error(HG_ERR_UNSUPPORTED, "prefix: row counts must fit int32");
   (void)max_k_len;
   PrefixParams p;
@@ -194,6 +208,7 @@ int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, f
   p.hq = hq; p.hkv = hkv; p.d = d;
   p.q_stride_row = q_stride_row; p.kv_stride_row = kv_stride_row;
   p.scale_log2 = sm_scale * kLog2e;
+  p.kv_splits = kv_splits;
   return launch_prefix(p, dtype, (cudaStream_t)stream);
 }
 

@@ -177,8 +177,10 @@ struct PrefixParams {
   int hq, hkv, d;
   int64_t q_stride_row, kv_stride_row;
   float scale_log2;
+  int kv_splits;  // >= 1; out / lse then hold kv_splits partial results back to back
 };
 int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s);
+int suggest_prefix_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits);
 
 int launch_kv_append(const void* k_new, const void* v_new, const void* positions, int positions_i64, void* k_cache,
                      void* v_cache, int b, int nq, int lk, int hkv, int d, int dtype, cudaStream_t s);

@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     prefix_attn_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
                              T* __restrict__ out, float* __restrict__ lse, const int32_t* __restrict__ cu_seqlens_k,
-                             int q_per_group, int tiles_per_group, int k_len_uniform, int hq, int hkv, float scale_log2) {
+                             int q_per_group, int tiles_per_group, int k_len_uniform, int hq, int hkv, float scale_log2,
+                             int kv_splits, int n_q_rows) {
   using L = SmemLayout<D>;
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t kIdescQK = make_idesc(kFmt, 0, BLOCK_M, BLOCK_N);
@@ -285,7 +286,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   Barriers* bars = reinterpret_cast<Barriers*>(smem + L::kBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x, head = blockIdx.y;
+  // blockIdx.x = (group, m-tile, kv split): the splits of one tile sit next to each other
+  const int split = blockIdx.x % kv_splits;
+  const int tile = blockIdx.x / kv_splits, head = blockIdx.y;
   const int grp = tile / tiles_per_group, mt = tile % tiles_per_group;
   const int kvh = head / (hq / hkv);
   const int q_row0 = grp * q_per_group + mt * (kTiles * BLOCK_M);
@@ -298,6 +301,16 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else {
     k_start = grp * k_len_uniform;
     k_len = k_len_uniform;
+  }
+  if (kv_splits > 1) {
+    // split-KV: this CTA owns key blocks [split * bps, (split + 1) * bps) of its group and writes partial
+    // result number `split` (rows [split * n_q_rows, ...) of out / lse); the merge is the caller's combine.
+    const int bps = ((k_len + BLOCK_N - 1) / BLOCK_N + kv_splits - 1) / kv_splits;
+    const int first = split * bps * BLOCK_N;
+    k_start += first;
+    k_len = max(0, min(k_len - first, bps * BLOCK_N));
+    out += (int64_t)split * n_q_rows * hq * D;
+    if (lse != nullptr) lse += (int64_t)split * n_q_rows * hq;
   }
   const int n_blocks = (k_len + BLOCK_N - 1) / BLOCK_N;
 
@@ -641,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (t == 0) named_bar_sync<1, BLOCK_M>(); else named_bar_sync<2, BLOCK_M>();
         if (wq == 0 && lane == 0) {
 #pragma unroll
-          for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&tmap_o, stage + h * L::kQHalfBytes, head * D + h * 64, tile_row0);
+          for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&tmap_o, stage + h * L::kQHalfBytes, head * D + h * 64, split * n_q_rows + tile_row0);
           bulk_commit_and_wait();
         }
       } else {
@@ -710,7 +723,8 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   if ((rc = make_tmap(&tq, p.q, dtype, n_q_rows, (uint64_t)p.hq * D, p.q_stride_row, BLOCK_M)) != HG_OK) return rc;
   if ((rc = make_tmap(&tk, p.k, dtype, p.n_k_rows, (uint64_t)p.hkv * D, p.kv_stride_row, BLOCK_N)) != HG_OK) return rc;
   if ((rc = make_tmap(&tv, p.v, dtype, p.n_k_rows, (uint64_t)p.hkv * D, p.kv_stride_row, BLOCK_N)) != HG_OK) return rc;
-  if ((rc = make_tmap(&to, p.out, dtype, n_q_rows, (uint64_t)p.hq * D, (uint64_t)p.hq * D, BLOCK_M)) != HG_OK) return rc;
+  const int splits = p.kv_splits < 1 ? 1 : p.kv_splits;
+  if ((rc = make_tmap(&to, p.out, dtype, n_q_rows * splits, (uint64_t)p.hq * D, (uint64_t)p.hq * D, BLOCK_M)) != HG_OK) return rc;
   const int smem_bytes = L::kTotal + 1024;
   static bool attr_set = false;  // per instantiation; idempotent, racing threads set the same value
   if (!attr_set) {
@@ -719,9 +733,10 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
     attr_set = true;
   }
   const int tiles_per_group = (p.q_per_group + kTiles * BLOCK_M - 1) / (kTiles * BLOCK_M);
-  dim3 grid((unsigned)(p.n_groups * tiles_per_group), (unsigned)p.hq, 1);
+  dim3 grid((unsigned)(p.n_groups * tiles_per_group * splits), (unsigned)p.hq, 1);
   prefix_attn_sm100_kernel<T, D><<<grid, kThreads, smem_bytes, s>>>(tq, tk, tv, to, (T*)p.out, p.lse, p.cu_seqlens_k, p.q_per_group,
-                                                                     tiles_per_group, p.k_len, p.hq, p.hkv, p.scale_log2);
+                                                                     tiles_per_group, p.k_len, p.hq, p.hkv, p.scale_log2, splits,
+                                                                     (int)n_q_rows);
   return check_launch("prefix_attn_sm100");
 }
 
@@ -731,6 +746,19 @@ extern "C" int hg_debug_read_trace(long long* host_buf, int n) {
   return (int)cudaMemcpyFromSymbol(host_buf, g_trace, sizeof(long long) * (size_t)n);
 }
 #endif
+
+// Number of KV splits that brings the CTA count of a prefix launch close to the SM count without going
+// below 4 key blocks per CTA: the head-parallel ranks of a tensor-parallel run own few heads each.
+int suggest_prefix_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits) {
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const long long base = (long long)n_groups * ((q_per_group + kTiles * BLOCK_M - 1) / (kTiles * BLOCK_M)) * hq;
+  if (base <= 0) return 1;
+  const int n_blocks = (max_k_len + BLOCK_N - 1) / BLOCK_N;
+  int s = (int)(sms / base);
+  s = min(s, n_blocks / 4);
+  s = min(s, max_splits);
+  return s < 1 ? 1 : s;
+}
 
 int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
   if (p.n_groups == 0 || p.q_per_group == 0) return HG_OK;

@@ -79,18 +79,34 @@ def prefix_attention_grouped(
     cu_seqlens_k: Optional[Tensor] = None,
     max_seqlen_k: Optional[int] = None,
 ) -> Tuple[Tensor, Tensor]:
-    """The prefix branch proper: ``q [b, nq, hq, d]`` with the batch grouped contiguously by shared
+    outs, lses = prefix_attention_partials(q, k, v, n_groups, cu_seqlens_k, max_seqlen_k, max_splits=1)
+    return outs[0], lses[0]
+
+
+def prefix_attention_partials(
+    q: Tensor,
+    k: Tensor,
+    v: Tensor,
+    n_groups: int,
+    cu_seqlens_k: Optional[Tensor] = None,
+    max_seqlen_k: Optional[int] = None,
+    max_splits: int = 1,
+):
+    """``prefix_attention_grouped`` as a list of partial results: when the launch has too few (group, tile,
+    head) work items to fill the GPU -- the head-parallel ranks of a tensor-parallel run -- the keys are cut
+    into up to ``max_splits`` ranges (split-KV) and one ``(out, lse)`` pair per range is returned, to be
+    merged by the combine that follows anyway.  Returns (list of out, list of lse).
+    Each ``out [b, nq, hq, d]`` / ``lse [b, nq, hq]`` (fp32) is already in the layout the
+    combine consumes (hydragen/attention.py:276-280, 333-338 need no transpose here).
+
+    The prefix branch proper: ``q [b, nq, hq, d]`` with the batch grouped contiguously by shared
     parent (``b % n_groups == 0``), ``k, v`` either ``[n_groups, L, hkv, d]`` or, with
-    ``cu_seqlens_k`` (int32 ``[n_groups + 1]`` on device), packed ``[total, hkv, d]``.
-    Returns ``out [b, nq, hq, d]`` and ``lse [b, nq, hq]`` (fp32) -- already in the layout the
-    combine consumes (hydragen/attention.py:276-280, 333-338 need no transpose here)."""
+    ``cu_seqlens_k`` (int32 ``[n_groups + 1]`` on device), packed ``[total, hkv, d]``."""
     b, nq, hq, d = q.shape
     if n_groups < 1 or b % n_groups != 0:
         raise ValueError(f"batch {b} is not a multiple of the number of shared sequences {n_groups}")
     hkv = k.shape[-2]
     sm_scale = d**-0.5  # hydragen/flash.py:293
-    out = torch.empty((b, nq, hq, d), device=q.device, dtype=q.dtype)
-    lse = torch.empty((b, nq, hq), device=q.device, dtype=torch.float32)
     backend = _prefix_backend()
     use_tc = q.dtype in _TC_DTYPES and d in _TC_HEAD_DIMS and backend != "rowwise"
     if backend == "tcgen05" and not use_tc:
@@ -101,6 +117,12 @@ def prefix_attention_grouped(
             raise ValueError("varlen shared K/V must be [total, kvheads, d]")
         if cu_seqlens_k.dtype != torch.int32 or cu_seqlens_k.shape[0] != n_groups + 1:
             raise ValueError("cu_seqlens_k must be int32 of n_groups + 1 entries")
+    splits = 1
+    if use_tc and max_splits > 1:
+        k_max = int(max_seqlen_k) if (varlen and max_seqlen_k is not None) else (k.shape[0] if varlen else k.shape[1])
+        splits = _lib.prefix_suggest_splits(q.device, n_groups, (b // n_groups) * nq, hq, k_max, max_splits)
+    out = torch.empty((splits, b, nq, hq, d), device=q.device, dtype=q.dtype)
+    lse = torch.empty((splits, b, nq, hq), device=q.device, dtype=torch.float32)
     if use_tc:
         q_rs = _rows_view(q)
         if q_rs is None:
@@ -121,7 +143,7 @@ def prefix_attention_grouped(
             n_k_rows, k_len = k.shape[0] * k.shape[1], k.shape[1]
             max_k = k_len
         _lib.prefix_attn_fwd(q, k, v, out, lse, n_groups, (b // n_groups) * nq, n_k_rows, k_len, cu_seqlens_k, max_k,
-                             hq, hkv, d, q_rs, kv_rs, sm_scale)
+                             hq, hkv, d, q_rs, kv_rs, sm_scale, kv_splits=splits)
     else:
         # CUDA-core path (fp32, other head dims): every sequence walks its parent's keys.
         if not _inner_ok(q):
@@ -137,8 +159,8 @@ def prefix_attention_grouped(
         else:
             strides = (k.stride(0), k.stride(1), k.stride(2))
             lk = k.shape[1]
-        _lib.rowwise_attn_fwd(q, k, v, None, cu_seqlens_k, b // n_groups, False, out, lse, lk, strides, [], [], sm_scale)
-    return out, lse
+        _lib.rowwise_attn_fwd(q, k, v, None, cu_seqlens_k, b // n_groups, False, out[0], lse[0], lk, strides, [], [], sm_scale)
+    return [out[i] for i in range(splits)], [lse[i] for i in range(splits)]
 
 
 def flash_attention(q: Tensor, k: Tensor, v: Tensor, causal: bool = False) -> Tuple[Tensor, Tensor]:

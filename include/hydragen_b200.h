@@ -138,6 +138,24 @@ int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, f
                        int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype,
                        void* stream);
 
+/* Split-KV form of hg_prefix_attn_fwd for launches with few (group, m-tile, head) work items -- the
+ * head-parallel ranks of a tensor-parallel run (hydragen/tp.py:90-112) own Hq/N heads each: the keys of
+ * every group are cut into kv_splits contiguous ranges, each handled by its own CTAs, and kv_splits
+ * PARTIAL results are written back to back:
+ *   out [kv_splits, n_q_rows, hq, d],  lse [kv_splits, n_q_rows, hq]   (a split with no keys: out 0, lse -inf)
+ * to be merged by hg_combine_lse / the n_partials of hg_rowwise_attn_fwd / hg_decode_attn_fused (this is
+ * flash-attn's split-KV, whose heuristic the reference copies in hydragen/flash.py:37-73, with the reduce
+ * folded into the combine that follows anyway).  kv_splits == 1 is hg_prefix_attn_fwd. */
+int hg_prefix_attn_split_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
+                             int n_groups, int q_per_group, int64_t n_k_rows, int k_len,
+                             const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
+                             int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype,
+                             int kv_splits, void* stream);
+
+/* Suggested kv_splits (>= 1, <= max_splits) for a prefix launch on the device seen by hg_init:
+ * fills the SMs without going below 4 key blocks per CTA.  Host-side arithmetic only. */
+int hg_prefix_suggest_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits);
+
 /* ---------------------------------------------------------------------------------------
  * KV-cache append for one decode step ("next" row N1 of SURVEY.md 8f): writes the new key and
  * value row of every sequence at its own position.  Replaces the two scatter_ calls with a

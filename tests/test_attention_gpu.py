@@ -361,3 +361,49 @@ def test_hydragen_attention_decode_matches_unfused(sizes):
     ref = O.hydragen_attention(c["q"], k2.cpu(), v2.cpu(), c["shared_ks"], c["shared_vs"], c["shared_cu_seq_lens"], c["shared_max_seq_lens"],
                                c["use_varlens"], seq_lens=pos[:, 0] + 1)
     _assert_close(out1, ref, dtype, "fused vs oracle")
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("splits", [2, 3, 8])
+def test_prefix_split_kv_partials_merge_to_full(dtype, splits):
+    """Split-KV prefix launch (hg_prefix_attn_split_fwd): the merged partials == the unsplit result == oracle,
+    for uniform and ragged (varlen) groups, incl. splits that receive no keys (out 0, lse -inf)."""
+    from hydragen_b200 import _lib
+    from hydragen_b200.attention import combine_lse_cuda
+
+    g = torch.Generator().manual_seed(splits)
+    lens = [700, 65, 130, 1]  # ragged groups: the short ones leave later splits empty
+    n, qps, hq, hkv, d = len(lens), 40, 4, 2, 128
+    q = torch.randn(n * qps, 1, hq, d, generator=g).to(dtype)
+    k = torch.randn(sum(lens), hkv, d, generator=g).to(dtype)
+    v = torch.randn(sum(lens), hkv, d, generator=g).to(dtype)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    qd, kd, vd, cud = q.cuda(), k.cuda(), v.cuda(), cu.cuda()
+    out = torch.empty(splits, n * qps, 1, hq, d, device="cuda", dtype=dtype)
+    lse = torch.empty(splits, n * qps, 1, hq, device="cuda", dtype=torch.float32)
+    _lib.prefix_attn_fwd(qd, kd, vd, out, lse, n, qps, kd.shape[0], 0, cud, max(lens), hq, hkv, d, hq * d, hkv * d, d**-0.5, kv_splits=splits)
+    merged, mlse = combine_lse_cuda([out[i] for i in range(splits)], [lse[i] for i in range(splits)], return_lse=True)
+    torch.cuda.synchronize()
+    assert torch.isinf(lse).any() or splits == 2  # some (group, split) pairs are empty
+    cu_q = torch.arange(0, n + 1, dtype=torch.int32) * qps
+    ro, rl = O.flash_attention_varlen(q.view(n * qps, hq, d), k, v, cu_q, cu, qps, max(lens))
+    _assert_close(merged.view(n * qps, hq, d), ro, dtype, f"split-KV x{splits}")
+    rl = rl.permute(0, 2, 1).reshape(n * qps, hq)  # [n, h, qps] -> rows
+    assert (mlse.view(n * qps, hq).double().cpu() - rl).abs().max().item() < 5e-3
+
+
+def test_operator_uses_split_kv_when_few_heads():
+    """A head-parallel rank's shape (few local heads, long prefix): the operator picks kv_splits > 1 by itself and
+    the result still matches the oracle."""
+    from hydragen_b200 import _lib
+    from hydragen_b200.attention import hydragen_attention_nopad
+
+    g = torch.Generator().manual_seed(9)
+    b, hq, hkv, d, ls, lu = 256, 2, 1, 128, 1500, 8
+    mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16)
+    q, k, v, sk, sv = mk(b, 1, hq, d), mk(b, lu, hkv, d), mk(b, lu, hkv, d), mk(1, ls, hkv, d), mk(1, ls, hkv, d)
+    sl = torch.randint(1, lu + 1, (b,), generator=g)
+    assert _lib.prefix_suggest_splits(torch.device("cuda:0"), 1, b, hq, ls, 8) > 1
+    out = hydragen_attention_nopad(q.cuda(), k.cuda(), v.cuda(), [sk.cuda()], [sv.cuda()], seq_len=sl.cuda())
+    ref = O.hydragen_attention_nopad(q, k, v, [sk], [sv], seq_len=sl)
+    _assert_close(out, ref, torch.bfloat16, "auto split-KV")
