@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-model", action="store_true",
+                    help="also run scripts/full_model_decode.py (random-init Llama-2-7B generate, configs[2]) and attach its numbers")
     return ap.parse_args()
 
 
@@ -373,21 +375,27 @@ def run_ours(a):
         hv = [torch.randn(B, 1, HKV, D, dtype=dt).pin_memory() for _ in range(L)]
         ho = [torch.empty(B, 1, H, D, dtype=dt).pin_memory() for _ in range(L)]
 
+        from hydragen_b200.host import HostDecodeLayer, HostDecodePipeline
+
+        pipe = HostDecodePipeline(dev)
+        host_layers = [HostDecodeLayer(hq[i], hk[i], hv[i], ho[i], qs[i], kn[i], vn[i], uniq[i, 0], uniq[i, 1], [shared_k[i]], [shared_v[i]])
+                       for i in range(L)]
+        after = (lambda i: dist.all_reduce(proj[i])) if world > 1 else None
+
         def step_e2e():
-            for i in range(L):
-                qs[i].copy_(hq[i], non_blocking=True)
-                kn[i].copy_(hk[i], non_blocking=True)
-                vn[i].copy_(hv[i], non_blocking=True)
-                layer(i)
-                ho[i].copy_(outs[i], non_blocking=True)
+            pipe.step(host_layers, pos, after_layer=after)
 
         for _ in range(3):
             step_e2e()
+        pipe.synchronize()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for _ in range(a.e2e_steps):
             step_e2e()
+        compute_stream = torch.cuda.current_stream()
+        compute_stream.wait_stream(pipe.h2d)
+        compute_stream.wait_stream(pipe.d2h)  # the last download is inside the timed region
         f1.record()
         barrier()
         te = f0.elapsed_time(f1)
@@ -398,7 +406,8 @@ def run_ours(a):
         h2d = L * (B * H * D + 2 * B * HKV * D) * esz * world
         d2h = L * B * H * D * esz * world
         e2e = {"value": B / (te / a.e2e_steps / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": te / a.e2e_steps, "steps": a.e2e_steps}
+               "ms_per_step": te / a.e2e_steps, "steps": a.e2e_steps,
+               "api": "hydragen_b200.host.HostDecodePipeline.step: pinned host q/k_new/v_new -> H2D -> kernels -> D2H of out, per layer, 3 streams"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -406,6 +415,16 @@ def run_ours(a):
         cpu_baseline = {"value": B / (t_layer * L), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"1 of {L} layers of the same workload, fp32 torch, median of {n} runs (~{a.cpu_seconds:.0f} s); tokens/s extrapolated x{L}",
                         "ms_per_layer": t_layer * 1e3}
+
+    full_model = None
+    if a.full_model and world == 1:
+        del graph, step
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import full_model_decode
+
+        full_model = full_model_decode.run()
+        graph = step = None
 
     if rank == 0:
         line = {
@@ -418,6 +437,8 @@ def run_ours(a):
             "roofline": roofline, "roofline_suffix": roofline_suffix, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
         }
+        if full_model is not None:
+            line["full_model"] = full_model
         print(json.dumps(line), flush=True)
     if world > 1:
         # NCCL teardown can block while captured graphs still hold its kernels: drop them first, and never let

@@ -1,0 +1,85 @@
+"""Host-buffer entry point of the decode hot path: the caller's q / k_new / v_new live in pinned HOST memory and
+the attention output is wanted back on the host (an engine whose projections run elsewhere, or a measurement
+through the boundary with the copies included).  Per layer the work is
+
+    H2D(q, k_new, v_new)  ->  prefix launch(es) + fused append/suffix/combine launch  ->  D2H(out)
+
+and a decode step is that for every layer.  The three stages run on three streams and are chained per layer with
+events, so layer i+1's upload and layer i-1's download overlap layer i's kernels (PCIe is full duplex); a layer's
+staging buffers are only rewritten after the previous step's kernels of that layer have finished.  torch supplies
+streams, events and pinned memory; the kernels are the C-ABI library's.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from .attention import hydragen_attention_decode
+
+
+@dataclass
+class HostDecodeLayer:
+    """One layer's operands.  ``*_host`` are pinned host tensors, ``*_dev`` the device staging buffers of the
+    same shapes, the caches and shared K/V are resident on the device."""
+
+    q_host: Tensor
+    k_host: Tensor
+    v_host: Tensor
+    out_host: Tensor
+    q_dev: Tensor
+    k_dev: Tensor
+    v_dev: Tensor
+    k_cache: Tensor
+    v_cache: Tensor
+    shared_ks: List[Tensor]
+    shared_vs: List[Tensor]
+    shared_cu_seq_lens: Optional[List[Optional[Tensor]]] = None
+    shared_max_seq_lens: Optional[List[Optional[int]]] = None
+    use_varlens: Optional[List[bool]] = None
+    out_dev: Optional[Tensor] = field(default=None, repr=False)
+
+
+class HostDecodePipeline:
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.h2d = torch.cuda.Stream(device)
+        self.d2h = torch.cuda.Stream(device)
+        self._done: dict = {}  # layer index -> event: kernels of the previous step finished (staging reusable)
+
+    def step(self, layers: Sequence[HostDecodeLayer], positions: Tensor, after_layer=None) -> None:
+        """One decode step over ``layers``; ``positions [b]`` (device) = row of the new token in the unique
+        caches.  ``after_layer(i)`` (optional) is called on the compute stream after layer i's kernels (the
+        tensor-parallel all-reduce goes there).  Returns once everything is enqueued; ``out_host`` is valid
+        after ``synchronize()``."""
+        compute = torch.cuda.current_stream(self.device)
+        for i, ly in enumerate(layers):
+            with torch.cuda.stream(self.h2d):
+                ev = self._done.get(i)
+                if ev is not None:
+                    self.h2d.wait_event(ev)
+                ly.q_dev.copy_(ly.q_host, non_blocking=True)
+                ly.k_dev.copy_(ly.k_host, non_blocking=True)
+                ly.v_dev.copy_(ly.v_host, non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(self.h2d)
+            compute.wait_event(up)
+            ly.out_dev = hydragen_attention_decode(ly.q_dev, ly.k_dev, ly.v_dev, positions, ly.k_cache, ly.v_cache, ly.shared_ks, ly.shared_vs,
+                                                   ly.shared_cu_seq_lens, ly.shared_max_seq_lens, ly.use_varlens)
+            if after_layer is not None:
+                after_layer(i)
+            done = torch.cuda.Event()
+            done.record(compute)
+            self._done[i] = done
+            with torch.cuda.stream(self.d2h):
+                self.d2h.wait_event(done)
+                ly.out_host.copy_(ly.out_dev, non_blocking=True)
+                ly.out_dev.record_stream(self.d2h)
+
+    def synchronize(self) -> None:
+        self.h2d.synchronize()
+        self.d2h.synchronize()
+        torch.cuda.current_stream(self.device).synchronize()

@@ -407,3 +407,38 @@ def test_operator_uses_split_kv_when_few_heads():
     out = hydragen_attention_nopad(q.cuda(), k.cuda(), v.cuda(), [sk.cuda()], [sv.cuda()], seq_len=sl.cuda())
     ref = O.hydragen_attention_nopad(q, k, v, [sk], [sv], seq_len=sl)
     _assert_close(out, ref, torch.bfloat16, "auto split-KV")
+
+
+def test_host_decode_pipeline_matches_direct_calls():
+    """The host-buffer entry (pinned host q/k/v -> H2D -> kernels -> D2H on three streams) gives, layer by layer and
+    step after step, exactly what the device-resident call gives."""
+    from hydragen_b200.attention import hydragen_attention_decode
+    from hydragen_b200.host import HostDecodeLayer, HostDecodePipeline
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(21)
+    L, b, hq, hkv, d, ls, lk = 3, 96, 8, 4, 128, 200, 16
+    mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16)
+    layers, ref_state = [], []
+    for _ in range(L):
+        sk, sv = mk(1, ls, hkv, d).cuda(), mk(1, ls, hkv, d).cuda()
+        kc, vc = mk(b, lk, hkv, d), mk(b, lk, hkv, d)
+        layers.append(HostDecodeLayer(mk(b, 1, hq, d).pin_memory(), mk(b, 1, hkv, d).pin_memory(), mk(b, 1, hkv, d).pin_memory(),
+                                      torch.empty(b, 1, hq, d, dtype=torch.bfloat16).pin_memory(),
+                                      torch.empty(b, 1, hq, d, dtype=torch.bfloat16, device=dev), torch.empty(b, 1, hkv, d, dtype=torch.bfloat16, device=dev),
+                                      torch.empty(b, 1, hkv, d, dtype=torch.bfloat16, device=dev), kc.cuda(), vc.cuda(), [sk], [sv]))
+        ref_state.append((kc.cuda(), vc.cuda(), sk, sv))
+    pipe = HostDecodePipeline(dev)
+    for step in range(3):
+        pos = torch.full((b,), step, dtype=torch.int64, device=dev)
+        for ly in layers:  # new host inputs every step
+            ly.q_host.copy_(mk(b, 1, hq, d))
+            ly.k_host.copy_(mk(b, 1, hkv, d))
+            ly.v_host.copy_(mk(b, 1, hkv, d))
+        pipe.step(layers, pos)
+        pipe.synchronize()
+        for ly, (kc, vc, sk, sv) in zip(layers, ref_state):
+            ref = hydragen_attention_decode(ly.q_host.cuda(), ly.k_host.cuda(), ly.v_host.cuda(), pos, kc, vc, [sk], [sv])
+            torch.cuda.synchronize()
+            assert torch.equal(ly.out_host, ref.cpu())
+            assert torch.equal(ly.k_cache, kc) and torch.equal(ly.v_cache, vc)
