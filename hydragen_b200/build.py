@@ -35,7 +35,7 @@ NVCC_FLAGS = [
 # development only: e.g. HG_EXTRA_NVCC_FLAGS="-DHG_PREFIX_TRACE" builds a separate, instrumented library
 EXTRA_FLAGS = os.environ.get("HG_EXTRA_NVCC_FLAGS", "").split()
 if EXTRA_FLAGS:
-    OUT_DIR = os.path.join(PKG_DIR, "_C_dev")
+    OUT_DIR = os.path.join(PKG_DIR, "_C_dev_" + "".join(ch if ch.isalnum() else "_" for ch in "".join(EXTRA_FLAGS)).strip("_"))
     LIB_PATH = os.path.join(OUT_DIR, "libhydragen_b200.so")
 
 

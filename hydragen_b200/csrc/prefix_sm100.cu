@@ -50,6 +50,12 @@ constexpr uint32_t kTmemCols = 512;
 __host__ __device__ constexpr uint32_t tmem_s(int t, int b) { return (uint32_t)t * 128u + (uint32_t)b * 64u; }  // S_t buffer b (P aliases its first 32 columns)
 __host__ __device__ constexpr uint32_t tmem_o(int t) { return 256u + (uint32_t)t * 128u; }                       // O_t
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+#ifndef HG_PREFIX_EMU_EVERY
+#define HG_PREFIX_EMU_EVERY 0
+#endif
+// every n-th pair of exponentials is computed on the FMA pipes instead of MUFU (0: none).  Measured at cfg#2
+// (B200, graph-timed): 0 -> 35.1 us, 4 -> 36.1, 3 -> 36.0, 2 -> 36.2: the warps are issue-bound, not MUFU-bound.
+constexpr int kEmuEvery = HG_PREFIX_EMU_EVERY;
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -199,6 +205,58 @@ __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
+}
+
+// ---- packed fp32x2 arithmetic (sm_100: one issue slot for two lanes' worth of FMA-pipe work) -------------
+__device__ __forceinline__ uint64_t pack_f2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2_rm(uint64_t a, uint64_t b) {  // round toward -inf
+  uint64_t d;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// 2^x for a pair of fp32 on the FMA / ALU pipes instead of the MUFU unit (Cody-Waite split + degree-3
+// minimax polynomial, max relative error 8.8e-5 -- below the rounding of the 16-bit P it feeds):
+//   r = RM(x + 1.5*2^23) keeps floor(x) in its low mantissa bits, f = x - floor(x) in [0, 1),
+//   2^x = p(f) * 2^floor(x): the integer part is added straight into the exponent field of p(f).
+// Inputs are clamped at -127 (2^x underflows there anyway; without it the exponent field would wrap).
+__device__ __forceinline__ void exp2_poly_x2(float x0, float x1, float& p0, float& p1) {
+  const uint64_t kMagic = pack_f2(12582912.f, 12582912.f);
+  const uint64_t kC3 = pack_f2(0.077119089663028717041015625f, 0.077119089663028717041015625f);
+  const uint64_t kC2 = pack_f2(0.227564394474029541015625f, 0.227564394474029541015625f);
+  const uint64_t kC1 = pack_f2(0.695146143436431884765625f, 0.695146143436431884765625f);
+  const uint64_t kOne = pack_f2(1.f, 1.f);
+  const uint64_t x = pack_f2(fmaxf(x0, -127.f), fmaxf(x1, -127.f));
+  const uint64_t r = fadd2_rm(x, kMagic);
+  const uint64_t f = fsub2(x, fsub2(r, kMagic));
+  uint64_t p = ffma2(kC3, f, kC2);
+  p = ffma2(p, f, kC1);
+  p = ffma2(p, f, kOne);
+  float r0, r1, q0, q1;
+  unpack_f2(r, r0, r1);
+  unpack_f2(p, q0, q1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
 }
 
 #define HG_W16(a, o)                                                                                                     \
@@ -358,6 +416,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_base);
+  // The launch that follows on the stream (the fused append / suffix / combine kernel) is a programmatic
+  // dependent: let it start on SMs this grid leaves idle; it waits for this grid's completion itself
+  // before it reads the partial results written here.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // Register budget (setmaxnreg must sit inside the role branch it applies to): the producer
   // warpgroup gives registers back, the two softmax warpgroups (128 live fp32 scores per thread)
@@ -539,18 +601,30 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
         const float neg_mc = -m_used * scale_log2;
-        float ps[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[BLOCK_N / 2];
-        auto exp8 = [&](int g) {  // in place: score -> p
+        const uint64_t scale2 = pack_f2(scale_log2, scale_log2), neg2 = pack_f2(neg_mc, neg_mc);
+        uint64_t ps2[2] = {0ull, 0ull};  // packed row sums
+        auto exp8 = [&](int g) {  // in place: score -> p; every kEmuEvery-th pair goes to the FMA pipes
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            cur[g * 8 + c] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(cur[g * 8 + c]), scale_log2, neg_mc)));
+          for (int c = 0; c < 8; c += 2) {
+            float x0, x1;
+            unpack_f2(ffma2(pack_f2(__uint_as_float(cur[g * 8 + c]), __uint_as_float(cur[g * 8 + c + 1])), scale2, neg2), x0, x1);
+            float p0, p1;
+            if (kEmuEvery > 0 && ((c >> 1) % kEmuEvery) == kEmuEvery - 1) {
+              exp2_poly_x2(x0, x1, p0, p1);
+            } else {
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
+            cur[g * 8 + c] = __float_as_uint(p0);
+            cur[g * 8 + c + 1] = __float_as_uint(p1);
+          }
         };
         auto sum_pack8 = [&](int g) {
 #pragma unroll
           for (int c = 0; c < 8; c += 2) {
             const float p0 = __uint_as_float(cur[g * 8 + c]), p1 = __uint_as_float(cur[g * 8 + c + 1]);
-            ps[(c >> 1) & 3] += p0 + p1;
+            ps2[(c >> 1) & 1] = fadd2(ps2[(c >> 1) & 1], pack_f2(p0, p1));
             pk[(g * 8 + c) >> 1] = pack2<T>(p0, p1);
           }
         };
@@ -588,7 +662,11 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int g = 4; g < 8; ++g) max8(mx, nxt, g);
           m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
         }
-        l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+        {
+          float a0, a1;
+          unpack_f2(fadd2(ps2[0], ps2[1]), a0, a1);
+          l += a0 + a1;
+        }
         if (wq == 0 && lane == 0) HG_TRACE(1 + t, j, 4);
         tmem_wait_st();
         tc_fence_before();

@@ -20,6 +20,8 @@
 //
 // Algorithmic bytes per unit: 2 * len_b * D * sizeof(T) (K, V) + D * sizeof(T) * g*nq * (2 + n_partials)
 // (q, out, partial outs) + 4 * g*nq * (1 + n_partials) (LSEs).  Bound: HBM.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hg {
@@ -332,10 +334,11 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
   const int64_t orow0 = (int64_t)b_idx * p.hq + (int64_t)kvh * R;
   const int np = p.partials.n;
 
-  // independent of len: the query rows, the new K/V row and the first prefix partial (the common
-  // decode case is one shared level) are requested before the key loop so their latency overlaps it
-  uint4 qraw[R], p0raw[R];
-  float p0lse[R];
+  // independent of len: the query rows and the new K/V row are requested before the key loop so their
+  // latency overlaps it.  (The prefix partials are only touched after the key loop, behind
+  // griddepcontrol.wait: this kernel is launched as the programmatic dependent of the prefix launch and
+  // does its own K/V work while that one drains.)
+  uint4 qraw[R];
   uint4 knew = make_uint4(0, 0, 0, 0), vnew = make_uint4(0, 0, 0, 0);
   if constexpr (kFused) {
     if (valid) {
@@ -347,15 +350,8 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     qraw[r] = make_uint4(0, 0, 0, 0);
-    p0raw[r] = make_uint4(0, 0, 0, 0);
-    p0lse[r] = -INFINITY;
-    if (valid) {
+    if (valid)
       qraw[r] = ld_v4(reinterpret_cast<const T*>(p.q) + (int64_t)b_idx * p.q_stride_b + (int64_t)(kvh * R + r) * p.q_stride_h + dl * VEC);
-      if (np > 0) {
-        p0raw[r] = ld_stream_v4(reinterpret_cast<const T*>(p.partials.outs[0]) + (orow0 + r) * D + dl * VEC);
-        p0lse[r] = __ldg(p.partials.lses[0] + orow0 + r);
-      }
-    }
   }
   int len_max = len, len_min = valid ? len : 0x7fffffff;
 #pragma unroll
@@ -479,7 +475,20 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
   }
   if constexpr (kFused) absorb(knew, vnew, valid);
 
+  // everything above is independent of the prefix launch(es); their partial results are read from here on
+  if (np > 0) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (!valid) return;
+  uint4 p0raw[R];
+  float p0lse[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    p0raw[r] = make_uint4(0, 0, 0, 0);
+    p0lse[r] = -INFINITY;
+    if (np > 0) {
+      p0raw[r] = ld_v4(reinterpret_cast<const T*>(p.partials.outs[0]) + (orow0 + r) * D + dl * VEC);
+      p0lse[r] = *(p.partials.lses[0] + orow0 + r);
+    }
+  }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int64_t orow = orow0 + r;
@@ -492,7 +501,7 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
     if (np > 0) {
       // merge with the prefix partials: first one prefetched, further shared levels one by one
       float mx = fmaxf(lse, p0lse[r]);
-      for (int i = 1; i < np; ++i) mx = fmaxf(mx, __ldg(p.partials.lses[i] + orow));
+      for (int i = 1; i < np; ++i) mx = fmaxf(mx, *(p.partials.lses[i] + orow));
       const float mx_safe = (mx == -INFINITY) ? 0.f : mx;
       const float w_s = __expf(lse - mx_safe);
       float den = w_s;
@@ -507,10 +516,10 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
         for (int e = 0; e < VEC; ++e) o[e] = fmaf(w, f[e], o[e]);
       }
       for (int i = 1; i < np; ++i) {
-        const float w = __expf(__ldg(p.partials.lses[i] + orow) - mx_safe);
+        const float w = __expf(*(p.partials.lses[i] + orow) - mx_safe);
         den += w;
         float f[VEC];
-        Vec16<T>::unpack(ld_stream_v4(reinterpret_cast<const T*>(p.partials.outs[i]) + orow * D + dl * VEC), f);
+        Vec16<T>::unpack(ld_v4(reinterpret_cast<const T*>(p.partials.outs[i]) + orow * D + dl * VEC), f);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) o[e] = fmaf(w, f[e], o[e]);
       }
@@ -524,6 +533,15 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
   }
 }
 
+// HYDRAGEN_B200_PDL=0 turns programmatic dependent launch off (debugging aid; read once)
+static bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("HYDRAGEN_B200_PDL");
+    return !(v != nullptr && v[0] == '0');
+  }();
+  return on;
+}
+
 template <typename T, int D, int R>
 static int launch_decode_slot(const RowwiseParams& p, cudaStream_t s) {
   constexpr int VEC = Vec16<T>::VEC;
@@ -532,10 +550,28 @@ static int launch_decode_slot(const RowwiseParams& p, cudaStream_t s) {
   const int64_t n_units = (int64_t)p.b * p.hkv;
   const int64_t blocks = (n_units + SLOTS - 1) / SLOTS;
   if (blocks > 0x7fffffffLL) return set_error(HG_ERR_UNSUPPORTED, "rowwise: too many units (%lld)", (long long)n_units);
+  // With prefix partials to merge this launch is the programmatic dependent of the launch before it on the
+  // stream (the prefix kernel): it may start while that one drains and blocks at griddepcontrol.wait only
+  // before it reads the partials.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (p.partials.n > 0 && pdl_enabled()) ? 1 : 0;
+  cudaError_t e;
   if (p.k_new != nullptr)
-    decode_slot_kernel<T, D, R, 4, MINB, true><<<(unsigned)blocks, 256, 0, s>>>(p);
+    e = cudaLaunchKernelEx(&cfg, decode_slot_kernel<T, D, R, 4, MINB, true>, p);
   else
-    decode_slot_kernel<T, D, R, 4, MINB, false><<<(unsigned)blocks, 256, 0, s>>>(p);
+    e = cudaLaunchKernelEx(&cfg, decode_slot_kernel<T, D, R, 4, MINB, false>, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(HG_ERR_CUDA, "decode_slot_attn: launch failed: %s", cudaGetErrorString(e));
+  }
   return check_launch("decode_slot_attn");
 }
 

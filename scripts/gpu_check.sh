@@ -9,7 +9,7 @@ run() { # name timeout cmd...
   timeout $t "$@" > gpurun_out/$name.log 2>&1
   echo "exit $? : $(tail -n 3 gpurun_out/$name.log | tr '\n' ' ' | cut -c1-400)" | tee -a gpurun_out/summary.txt
 }
-run tests 1500 python -m pytest tests -q -m gpu -p no:cacheprovider --timeout 300 --timeout-method thread
+run tests 400 python -m pytest tests -q -m gpu -p no:cacheprovider --timeout 90 --timeout-method thread
 run smoke 300 python __graft_entry__.py smoke
 run quick_bench 300 python scripts/quick_bench.py
 cat gpurun_out/summary.txt
