@@ -564,10 +564,15 @@ static int launch_decode_slot(const RowwiseParams& p, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = (p.partials.n > 0 && pdl_enabled()) ? 1 : 0;
   cudaError_t e;
+  // Short caches (the first decode steps, the microbenchmark): the work per unit is a handful of dependent
+  // memory round trips, so what matters is how many units are resident -- 2 keys per trip, half the registers.
+  const bool small = p.lk <= 32 && R <= 2;
   if (p.k_new != nullptr)
-    e = cudaLaunchKernelEx(&cfg, decode_slot_kernel<T, D, R, 4, MINB, true>, p);
+    e = small ? cudaLaunchKernelEx(&cfg, decode_slot_kernel<T, D, R, 2, (R == 1 ? 4 : 3), true>, p)
+              : cudaLaunchKernelEx(&cfg, decode_slot_kernel<T, D, R, 4, MINB, true>, p);
   else
-    e = cudaLaunchKernelEx(&cfg, decode_slot_kernel<T, D, R, 4, MINB, false>, p);
+    e = small ? cudaLaunchKernelEx(&cfg, decode_slot_kernel<T, D, R, 2, (R == 1 ? 4 : 3), false>, p)
+              : cudaLaunchKernelEx(&cfg, decode_slot_kernel<T, D, R, 4, MINB, false>, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(HG_ERR_CUDA, "decode_slot_attn: launch failed: %s", cudaGetErrorString(e));
