@@ -241,20 +241,32 @@ def run_ours(a):
     vn = [mk(B, 1, HKV, D) for _ in range(L)]
     pos = torch.full((B, 1), a.suffix_len - 1, device=dev, dtype=torch.int64)  # row of the new token
     seq_lens = pos[:, 0] + 1
-    proj = [torch.zeros(B, hidden, device=dev, dtype=dt) for _ in range(L)] if world > 1 else None
+    # the collective of the path: all-reduce(sum) of the row-parallel o_proj output [B, hidden], one per layer
+    # (hydragen/tp.py:108-112) -- the library's NVLS kernel on symmetric memory where the platform has NVLink
+    # multicast, else NCCL
+    proj, nvls = None, None
+    if world > 1:
+        from hydragen_b200.collectives import make_all_reduce
+
+        nvls = None if os.environ.get("HG_BENCH_NCCL") else make_all_reduce(L * (B * hidden * 2 + 256), dev)
+        if nvls is not None:
+            proj = [nvls.buffer((B, hidden), dt).zero_() for _ in range(L)]
+        else:
+            proj = [torch.zeros(B, hidden, device=dev, dtype=dt) for _ in range(L)]
+    all_reduce = (lambda t: nvls.all_reduce_(t)) if nvls is not None else (lambda t: dist.all_reduce(t))
     outs = [None] * L
 
     def layer(i):
         # prefix launch (tcgen05) + ONE launch for KV append + suffix attention + combine
         outs[i] = hydragen_attention_decode(qs[i], kn[i], vn[i], pos, uniq[i, 0], uniq[i, 1], [shared_k[i]], [shared_v[i]])
         if world > 1:
-            dist.all_reduce(proj[i])  # the one collective per attention layer (hydragen/tp.py:108-112)
+            all_reduce(proj[i])  # the one collective per attention layer (hydragen/tp.py:108-112)
 
     def step_eager():
         for i in range(L):
             layer(i)
 
-    launches_per_step = L * 2  # prefix + fused append/suffix/combine (NCCL kernels not counted)
+    launches_per_step = L * (2 + (1 if nvls is not None else 0))  # prefix + fused append/suffix/combine (+ our all-reduce kernel; NCCL's not counted)
 
     _log("inputs ready; eager warm-up")
     for _ in range(3):
@@ -380,7 +392,7 @@ def run_ours(a):
         pipe = HostDecodePipeline(dev)
         host_layers = [HostDecodeLayer(hq[i], hk[i], hv[i], ho[i], qs[i], kn[i], vn[i], uniq[i, 0], uniq[i, 1], [shared_k[i]], [shared_v[i]])
                        for i in range(L)]
-        after = (lambda i: dist.all_reduce(proj[i])) if world > 1 else None
+        after = (lambda i: all_reduce(proj[i])) if world > 1 else None
 
         def step_e2e():
             pipe.step(host_layers, pos, after_layer=after)
@@ -431,7 +443,7 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(a), "scope": "attention hot path of one decode step (prefix + fused kv-append/suffix/combine per layer); projections/MLP/sampling out of scope",
-                       "parallelism": f"tp{world} (head axis, 1 NCCL all-reduce of [B,{hidden}] bf16 per layer)" if world > 1 else "single GPU",
+                       "parallelism": (f"tp{world} (head axis, 1 all-reduce of [B,{hidden}] bf16 per layer: " + ("hg_allreduce_multimem NVLS kernel" if nvls is not None else "NCCL") + ")") if world > 1 else "single GPU",
                        "l2": f"inputs larger than L2: {L} layers x distinct caches cycle {L * (2 * a.prefix_len * HKV * D * 2 + 4 * B * H * D * 2) / 2**20:.0f}+ MiB per step through a 126 MB L2",
                        "cuda_graph": graph is not None},
             "roofline": roofline, "roofline_suffix": roofline_suffix, "cpu_baseline": cpu_baseline, "e2e": e2e,

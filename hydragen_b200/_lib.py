@@ -53,6 +53,7 @@ SYMBOLS = {
          c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64,
          _c_void_pp, _c_void_pp, c_int, c_float, c_int, c_void_p],
     ),
+    "hg_allreduce_multimem": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
     "hg_kv_append": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
@@ -225,3 +226,12 @@ def decode_attn_fused(q, k_new, v_new, positions, k_cache, v_cache, out, lse, pa
             b, lk, hq, hkv, d, q.stride(0), q.stride(2), k_cache.stride(0), k_cache.stride(1), k_cache.stride(2),
             _ptr_table(partial_outs), _ptr_table(partial_lses), len(partial_outs), float(sm_scale), dtype_code(q.dtype), _stream(q))
     _check(rc, "hg_decode_attn_fused")
+
+
+def allreduce_multimem(mc_ptr: int, out_ptr: int, flags_dev: int, rank: int, world: int, nbytes: int, dtype: torch.dtype, n_blocks: int,
+                       device) -> None:
+    ensure_init(device)
+    with torch.cuda.device(device):
+        rc = load().hg_allreduce_multimem(c_void_p(mc_ptr), c_void_p(out_ptr), c_void_p(flags_dev), rank, world, nbytes, dtype_code(dtype), n_blocks,
+                                          c_void_p(torch.cuda.current_stream(device).cuda_stream))
+    _check(rc, "hg_allreduce_multimem")

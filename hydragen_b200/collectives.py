@@ -1,0 +1,85 @@
+"""The collective that follows the attention hot path under head-axis tensor parallelism: all-reduce(sum) of the
+row-parallel o_proj output, one per attention layer (hydragen/tp.py:108-112).
+
+``MultimemAllReduce`` runs it as the library's own NVLS kernel (csrc/allreduce.cu: multimem.ld_reduce / multimem.st
+through the NVSwitch) on buffers that live in symmetric memory; torch supplies the plumbing (symmetric allocation,
+rendezvous, multicast mapping: ``torch.distributed._symmetric_memory``).  Where the platform has no multicast
+support the caller keeps using ``torch.distributed.all_reduce`` (NCCL) -- ``MultimemAllReduce.available`` says which.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class MultimemAllReduce:
+    def __init__(self, nbytes: int, device: torch.device, group=None, n_blocks: int = 128):
+        """Collective over ``group`` (default: world) for messages carved out of one symmetric arena of ``nbytes``."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.device = device
+        self.n_blocks = n_blocks
+        name = self.group.group_name
+        self.arena = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self._h = symm_mem.rendezvous(self.arena, name)
+        self.flags = symm_mem.empty(n_blocks * self.world, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self._hf = symm_mem.rendezvous(self.flags, name)
+        self.mc_base = int(self._h.multicast_ptr or 0)  # 0: no multicast mapping on this platform
+        self.flags_dev = int(self._hf.buffer_ptrs_dev)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+        self._used = 0
+
+    @property
+    def available(self) -> bool:
+        return self.mc_base != 0
+
+    def buffer(self, shape, dtype: torch.dtype) -> torch.Tensor:
+        """A tensor inside the symmetric arena (same offset on every rank, 256-byte aligned)."""
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        off = (self._used + 255) // 256 * 256
+        if off + nbytes > self.arena.numel():
+            raise ValueError("symmetric arena exhausted")
+        self._used = off + nbytes
+        return self.arena[off : off + nbytes].view(dtype).view(*shape)
+
+    def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum over the group of a tensor obtained from ``buffer()`` (contiguous)."""
+        off = t.data_ptr() - self.arena.data_ptr()
+        nbytes = t.numel() * t.element_size()
+        assert 0 <= off and off + nbytes <= self.arena.numel() and t.is_contiguous(), "tensor must come from buffer()"
+        assert self.available, "no NVLink multicast mapping on this platform: use torch.distributed.all_reduce"
+        _lib.allreduce_multimem(self.mc_base + off, 0, self.flags_dev, self.rank, self.world, nbytes, t.dtype, self.n_blocks, self.device)
+        return t
+
+    def all_reduce(self, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Out-of-place sum (one-shot form: one cross-rank barrier): ``t`` from ``buffer()``, result in a private
+        tensor.  ``t`` may be overwritten once a later collective of this object has completed."""
+        off = t.data_ptr() - self.arena.data_ptr()
+        nbytes = t.numel() * t.element_size()
+        assert 0 <= off and off + nbytes <= self.arena.numel() and t.is_contiguous(), "tensor must come from buffer()"
+        assert self.available, "no NVLink multicast mapping on this platform: use torch.distributed.all_reduce"
+        if out is None:
+            out = torch.empty_like(t)
+        _lib.allreduce_multimem(self.mc_base + off, out.data_ptr(), self.flags_dev, self.rank, self.world, nbytes, t.dtype, self.n_blocks, self.device)
+        return out
+
+
+def make_all_reduce(nbytes: int, device: torch.device, group=None) -> Optional[MultimemAllReduce]:
+    """The NVLS collective if this process group / platform supports it, else None (caller falls back to NCCL)."""
+    try:
+        ar = MultimemAllReduce(nbytes, device, group)
+        return ar if ar.available else None
+    except Exception:
+        return None

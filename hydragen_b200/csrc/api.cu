@@ -212,6 +212,18 @@ int hg_prefix_attn_split_fwd(const void* q, const void* k, const void* v, void* 
   return launch_prefix(p, dtype, (cudaStream_t)stream);
 }
 
+int hg_allreduce_multimem(void* mc_ptr, void* out, const void* flags_dev, int rank, int world, int64_t nbytes, int dtype,
+                          int n_blocks, void* stream) {
+  if (!valid_dtype(dtype)) return set_error(HG_ERR_INVALID_ARGUMENT, "allreduce: unknown dtype %d", dtype);
+  if (world < 2 || world > 32 || rank < 0 || rank >= world) return set_error(HG_ERR_INVALID_ARGUMENT, "allreduce: rank %d of %d", rank, world);
+  if (mc_ptr == nullptr || flags_dev == nullptr) return set_error(HG_ERR_INVALID_ARGUMENT, "allreduce: null pointer (no multicast mapping?)");
+  if (nbytes < 0 || nbytes % 16 != 0 || reinterpret_cast<uintptr_t>(mc_ptr) % 16 != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0)
+    return set_error(HG_ERR_UNSUPPORTED, "allreduce: size and address must be multiples of 16 bytes");
+  if (n_blocks < 1 || n_blocks > 1024) return set_error(HG_ERR_INVALID_ARGUMENT, "allreduce: n_blocks = %d", n_blocks);
+  if (nbytes == 0) return HG_OK;
+  return launch_allreduce_multimem(mc_ptr, out, flags_dev, rank, world, nbytes, dtype, n_blocks, (cudaStream_t)stream);
+}
+
 int hg_kv_append(const void* k_new, const void* v_new, const void* positions, int positions_i64, void* k_cache, void* v_cache,
                  int b, int nq, int lk, int hkv, int d, int dtype, void* stream) {
   if (!valid_dtype(dtype)) return set_error(HG_ERR_INVALID_ARGUMENT, "kv_append: unknown dtype %d", dtype);

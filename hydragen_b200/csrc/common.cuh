@@ -182,6 +182,9 @@ struct PrefixParams {
 int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s);
 int suggest_prefix_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits);
 
+int launch_allreduce_multimem(void* mc_ptr, void* out, const void* flags_dev, int rank, int world, int64_t nbytes, int dtype,
+                              int n_blocks, cudaStream_t s);
+
 int launch_kv_append(const void* k_new, const void* v_new, const void* positions, int positions_i64, void* k_cache,
                      void* v_cache, int b, int nq, int lk, int hkv, int d, int dtype, cudaStream_t s);
 

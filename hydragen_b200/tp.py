@@ -54,12 +54,42 @@ def shard_state_dict(sd: Dict[str, Tensor], rank: int, world_size: int) -> Dict[
 
 
 class _AllReduce:
-    """Sum over the tensor-parallel group, in place on the compute stream."""
+    """Sum over the tensor-parallel group on the compute stream.  On CUDA with NVLink multicast the library's
+    NVLS kernel (csrc/allreduce.cu) on a symmetric staging buffer; otherwise ``torch.distributed.all_reduce``
+    (NCCL on GPUs without multicast, gloo in the CPU tests).  Shared by every layer of a model: one staging
+    buffer per message size, set up on first use (the warm-up runs before a CUDA-graph capture)."""
 
-    def __init__(self, group=None):
+    _nvls: Dict[tuple, object] = {}
+
+    def __init__(self, group=None, use_nvls: bool = True):
         self.group = group
+        self.use_nvls = use_nvls
+
+    def _staging(self, x: Tensor):
+        key = (x.device, x.dtype, tuple(x.shape), id(self.group))
+        if key not in _AllReduce._nvls:
+            entry = None
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the NVLS all-reduce must be set up before CUDA-graph capture (run one eager step first)")
+            try:
+                from .collectives import make_all_reduce
+
+                ar = make_all_reduce(x.numel() * x.element_size() + 256, x.device, self.group)
+                if ar is not None:
+                    entry = (ar, ar.buffer(tuple(x.shape), x.dtype))
+            except Exception:
+                entry = None
+            _AllReduce._nvls[key] = entry
+        return _AllReduce._nvls[key]
 
     def __call__(self, x: Tensor) -> Tensor:
+        if self.use_nvls and x.is_cuda and dist.get_backend(self.group) == "nccl":
+            entry = self._staging(x)
+            if entry is not None:
+                ar, buf = entry
+                buf.copy_(x)
+                ar.all_reduce_(buf)
+                return buf
         dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
         return x
 

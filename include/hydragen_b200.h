@@ -191,6 +191,23 @@ int hg_decode_attn_fused(const void* q, const void* k_new, const void* v_new, co
                          const void* const* partial_outs_host, const float* const* partial_lses_host,
                          int n_partials, float sm_scale, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * In-place all-reduce(sum) of a buffer that every rank holds in symmetric memory mapped at one NVLink
+ * multicast address (NVLS: the NVSwitch reduces and broadcasts).  Replaces the NCCL all-reduce of the
+ * row-parallel o_proj output, one per attention layer (hydragen/tp.py:108-112), for the decode-step message
+ * sizes (4-20 MiB), where a ring is latency-bound.
+ *   mc_ptr     multicast address of the first byte to reduce (same offset on every rank; 16-byte aligned)
+ *   out        NULL: in place, two-shot (rank r reduces slice r and multicasts it back; two barriers);
+ *              else a private (non-symmetric) output buffer of nbytes: one-shot (every rank reduces the whole
+ *              message through the switch; one barrier) -- the input buffer may be overwritten only after a
+ *              later call of either form has completed
+ *   flags_dev  DEVICE array of `world` pointers: flags_dev[p] = rank p's flag array (uint32, zero-initialised
+ *              once, >= n_blocks * world entries), reachable through NVLink peer access
+ *   nbytes     message size, a multiple of 16;  n_blocks  CTAs to use (the same on every rank, <= SM count)
+ * Every rank of the group must enqueue the same call in the same order.  CUDA-graph capturable. */
+int hg_allreduce_multimem(void* mc_ptr, void* out, const void* flags_dev, int rank, int world,
+                          int64_t nbytes, int dtype, int n_blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
