@@ -7,28 +7,32 @@
 // Inter-sequence batching makes this a dense problem: for one (group, head) the queries of every
 // sequence sharing the prefix form Q[q_per_group x d] and are multiplied against the single
 // K,V[k_len x d] of that prefix.  One CTA owns TWO 128-row Q tiles (A, B) of one head and streams
-// the prefix in 128-key blocks; the two tiles ping-pong so that the tensor pipe works on one tile
-// while the softmax warps work on the other, and every K/V block fetched feeds 256 query rows:
+// the prefix in 64-key blocks; every K/V block fetched feeds 256 query rows, and the score block of
+// each tile is double buffered in TMEM so that Q K^T runs two blocks ahead of the softmax:
 //
-//   warp 0 (1 lane)  TMA producer: Q_A, Q_B once, then K_j / V_j into 2-deep smem rings
-//                    (cp.async.bulk.tensor, SWIZZLE_128B boxes of 128 rows x 64 elements)
-//   warp 1 (1 lane)  MMA issuer, per key block j:  PV_A(j)  QK_A(j+1)  PV_B(j)  QK_B(j+1)
-//                      S_t = Q_t K_j^T  (SS form, both operands K-major in smem, 128x128x16 per
+//   TMEM (512 columns)  S_A[0] S_A[1] S_B[0] S_B[1] (64 fp32 columns each) | O_A | O_B (128 each);
+//                       P_t(j) (16-bit) is written back over the first 32 columns of its S buffer
+//   warp 0 (1 lane)  TMA producer: Q_A, Q_B once, then a 4-deep ring whose slot u holds what MMA
+//                    iteration u consumes: V_u and K_{u+2} (cp.async.bulk.tensor, SWIZZLE_128B boxes)
+//   warps 1, 3       MMA issuer of tile A / B (all lanes walk the loop so descriptors stay in uniform
+//                    registers; one elected lane issues).  Per key block j:  PV_t(j)  QK_t(j+2)
+//                      S_t = Q_t K_j^T  (SS form, both operands K-major in smem, 128x64x16 per
 //                                        instruction, fp32 accumulate in TMEM)
 //                      O_t += P_t V_j   (TS form: P_t read from TMEM as the A operand, V_j straight
 //                                        from its row-major smem tile as an MN-major B operand --
 //                                        no transpose pass)
-//   warp 2           TMEM allocator (512 columns: S_A | S_B | O_A | O_B)
+//   warp 2           TMEM allocator
 //   warps 4-7        softmax of tile A, warps 8-11 softmax of tile B: thread t owns row t
-//                    (tcgen05.ld 32x32b: lane == row, so the row max / row sum need no shuffles),
-//                    exp2 with the scale folded into one FFMA, P_t written back over S_t in TMEM as
-//                    packed 16-bit, lazy rescale of O_t (only when the running max grows by more
-//                    than 2^8), epilogue O_t / l -> swizzled smem (the dead Q_t tile) -> TMA store,
-//                    LSE written directly in [b, nq, hq].
+//                    (tcgen05.ld 32x32b: lane == row, so the row max / row sum need no shuffles);
+//                    software pipelined: the scores of block j+1 are fetched and reduced to their
+//                    row max behind the MUFU exp2 requests of block j; scale / subtract / row sums as
+//                    packed fp32x2; P_t stored to TMEM as packed 16-bit; lazy rescale of O_t (only
+//                    when the running max grows by more than 2^8); epilogue O_t / l -> swizzled
+//                    smem (the dead Q_t tile) -> TMA store; LSE written directly in [b, nq, hq].
 //
 // All producer/consumer edges are mbarriers (TMA complete_tx, tcgen05.commit, thread arrives); there
-// is no __syncthreads in the main loop.  tcgen05.commit covers every MMA issued before it, so the
-// arrival of S_t(j) also tells the softmax warps that PV_t(j-1) has retired (O_t is stable).
+// is no __syncthreads in the main loop.  Split-KV (kv_splits > 1): the CTAs of one tile each take a
+// contiguous range of key blocks and write their own partial (out, lse).
 //
 // Algorithmic work per CTA: 4 * rows * k_len * d FLOP.  Bound: tensor pipe (AI ~ 680 FLOP/B at the
 // 7B config), with the MUFU exp2 rate (16/clk/SM == the 128x128x128 MMA rate) the co-limiter.
