@@ -1,6 +1,7 @@
 // C ABI of hydragen_b200 (see include/hydragen_b200.h): argument validation, error plumbing and
 // device bring-up.  No torch types, no allocation, no synchronisation on any launch path.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -31,6 +32,15 @@ int check_launch(const char* what) {
 }
 
 const DeviceInfo& device_info() { return g_info; }
+
+// HYDRAGEN_B200_PDL=0 turns programmatic dependent launch off (debugging aid; read once)
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("HYDRAGEN_B200_PDL");
+    return !(v != nullptr && v[0] == '0');
+  }();
+  return on;
+}
 
 static bool valid_dtype(int dtype) { return dtype == HG_F16 || dtype == HG_BF16 || dtype == HG_F32; }
 

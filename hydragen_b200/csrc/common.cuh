@@ -24,6 +24,7 @@ struct DeviceInfo {
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime
 };
 const DeviceInfo& device_info();
+bool pdl_enabled();  // programmatic dependent launch between the kernels of a decode step
 
 // ---- 16-byte vector of T <-> fp32 --------------------------------------------------------
 template <typename T>

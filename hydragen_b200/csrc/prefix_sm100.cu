@@ -424,6 +424,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   // dependent: let it start on SMs this grid leaves idle; it waits for this grid's completion itself
   // before it reads the partial results written here.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // This launch is itself a programmatic dependent of whatever precedes it on the stream (the previous
+  // layer's decode kernel, or the projection that produced q): everything above -- barrier init, TMEM
+  // allocation, descriptor prefetch -- overlapped its tail; q is read and out / lse are written only
+  // from here on.  (No-op when launched without the attribute.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // Register budget (setmaxnreg must sit inside the role branch it applies to): the producer
   // warpgroup gives registers back, the two softmax warpgroups (128 live fp32 scores per thread)
@@ -815,10 +820,22 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
     attr_set = true;
   }
   const int tiles_per_group = (p.q_per_group + kTiles * BLOCK_M - 1) / (kTiles * BLOCK_M);
-  dim3 grid((unsigned)(p.n_groups * tiles_per_group * splits), (unsigned)p.hq, 1);
-  prefix_attn_sm100_kernel<T, D><<<grid, kThreads, smem_bytes, s>>>(tq, tk, tv, to, (T*)p.out, p.lse, p.cu_seqlens_k, p.q_per_group,
-                                                                     tiles_per_group, p.k_len, p.hq, p.hkv, p.scale_log2, splits,
-                                                                     (int)n_q_rows);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(p.n_groups * tiles_per_group * splits), (unsigned)p.hq, 1);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, prefix_attn_sm100_kernel<T, D>, tq, tk, tv, to, (T*)p.out, p.lse, p.cu_seqlens_k, p.q_per_group,
+                                     tiles_per_group, p.k_len, p.hq, p.hkv, p.scale_log2, splits, (int)n_q_rows);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(HG_ERR_CUDA, "prefix_attn_sm100: launch failed: %s", cudaGetErrorString(e));
+  }
   return check_launch("prefix_attn_sm100");
 }
 

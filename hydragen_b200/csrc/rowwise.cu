@@ -313,6 +313,8 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
   const bool valid = unit < n_units;
   const int b_idx = valid ? (int)(unit / p.hkv) : 0;
   const int kvh = valid ? (int)(unit % p.hkv) : 0;
+  // the next launch on the stream (the next layer's prefix kernel) may begin its set-up while this grid drains
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // keys read from the cache: [0, len); fused: the new token sits at row `len` and is not re-read
   int len = 0;
@@ -531,15 +533,6 @@ __global__ void __launch_bounds__(256, MINB) decode_slot_kernel(const RowwisePar
     st_v4(reinterpret_cast<T*>(p.out) + orow * D + dl * VEC, Vec16<T>::pack(o));
     if (p.lse != nullptr && dl == 0) p.lse[orow] = lse;
   }
-}
-
-// HYDRAGEN_B200_PDL=0 turns programmatic dependent launch off (debugging aid; read once)
-static bool pdl_enabled() {
-  static const bool on = [] {
-    const char* v = getenv("HYDRAGEN_B200_PDL");
-    return !(v != nullptr && v[0] == '0');
-  }();
-  return on;
 }
 
 template <typename T, int D, int R>

@@ -11,5 +11,5 @@ run() { # name timeout cmd...
 }
 run tests 400 python -m pytest tests -q -m gpu -p no:cacheprovider --timeout 90 --timeout-method thread
 run smoke 300 python __graft_entry__.py smoke
-run quick_bench 300 python scripts/quick_bench.py
+run microbench 300 python scripts/microbenchmark.py --pairs 1024:2048 --suffix 1,64
 cat gpurun_out/summary.txt
