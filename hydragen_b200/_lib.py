@@ -58,6 +58,11 @@ SYMBOLS = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     ),
+    "hg_rope_qk": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int,
+         c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p],
+    ),
 }
 
 _lib: Optional[ctypes.CDLL] = None
@@ -235,3 +240,19 @@ def allreduce_multimem(mc_ptr: int, out_ptr: int, flags_dev: int, rank: int, wor
         rc = load().hg_allreduce_multimem(c_void_p(mc_ptr), c_void_p(out_ptr), c_void_p(flags_dev), rank, world, nbytes, dtype_code(dtype), n_blocks,
                                           c_void_p(torch.cuda.current_stream(device).cuda_stream))
     _check(rc, "hg_allreduce_multimem")
+
+
+def rope_qk(q, k, q_out, k_out, cos_table, sin_table, positions, rows, hq, hkv, d, q_stride_row, k_stride_row,
+            q_out_stride_row, k_out_stride_row) -> None:
+    ensure_init(q.device)
+    if positions.dtype == torch.int64:
+        pi64 = 1
+    elif positions.dtype == torch.int32:
+        pi64 = 0
+    else:
+        raise ValueError(f"positions must be int32 or int64, got {positions.dtype}")
+    with torch.cuda.device(q.device):
+        rc = load().hg_rope_qk(_ptr(q), _ptr(k), _ptr(q_out), _ptr(k_out), _ptr(cos_table), _ptr(sin_table), _ptr(positions), pi64,
+                               rows, hq, hkv, d, q_stride_row, k_stride_row, q_out_stride_row, k_out_stride_row,
+                               cos_table.shape[0], dtype_code(q.dtype), _stream(q))
+    _check(rc, "hg_rope_qk")

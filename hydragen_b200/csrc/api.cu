@@ -246,4 +246,38 @@ int hg_kv_append(const void* k_new, const void* v_new, const void* positions, in
   return launch_kv_append(k_new, v_new, positions, positions_i64, k_cache, v_cache, b, nq, lk, hkv, d, dtype, (cudaStream_t)stream);
 }
 
+int hg_rope_qk(const void* q, const void* k, void* q_out, void* k_out, const void* cos_table, const void* sin_table,
+               const void* positions, int positions_i64, int64_t rows, int hq, int hkv, int d, int64_t q_stride_row,
+               int64_t k_stride_row, int64_t q_out_stride_row, int64_t k_out_stride_row, int64_t table_rows, int dtype,
+               void* stream) {
+  if (!valid_dtype(dtype)) return set_error(HG_ERR_INVALID_ARGUMENT, "rope: unknown dtype %d", dtype);
+  if (rows < 0 || hq < 0 || hkv < 0 || d < 2 || table_rows < 1)
+    return set_error(HG_ERR_INVALID_ARGUMENT, "rope: bad sizes rows=%lld hq=%d hkv=%d d=%d table_rows=%lld", (long long)rows, hq, hkv,
+                     d, (long long)table_rows);
+  const int vec = dtype == HG_F32 ? 4 : 8;
+  if (d % (2 * vec) != 0) return set_error(HG_ERR_UNSUPPORTED, "rope: head_dim %d must be a multiple of %d", d, 2 * vec);
+  if (rows > 0 && hq > 0 && (q == nullptr || q_out == nullptr)) return set_error(HG_ERR_INVALID_ARGUMENT, "rope: null q");
+  if (rows > 0 && hkv > 0 && (k == nullptr || k_out == nullptr)) return set_error(HG_ERR_INVALID_ARGUMENT, "rope: null k");
+  if (rows > 0 && (cos_table == nullptr || sin_table == nullptr || positions == nullptr))
+    return set_error(HG_ERR_INVALID_ARGUMENT, "rope: null table / positions");
+  if (q_stride_row % vec || k_stride_row % vec || q_out_stride_row % vec || k_out_stride_row % vec ||
+      reinterpret_cast<uintptr_t>(q) % 16 || reinterpret_cast<uintptr_t>(k) % 16 || reinterpret_cast<uintptr_t>(q_out) % 16 ||
+      reinterpret_cast<uintptr_t>(k_out) % 16 || reinterpret_cast<uintptr_t>(cos_table) % 16 ||
+      reinterpret_cast<uintptr_t>(sin_table) % 16)
+    return set_error(HG_ERR_UNSUPPORTED, "rope: bases and row strides must be 16-byte aligned");
+  if ((hq > 0 && (q_stride_row < (int64_t)hq * d || q_out_stride_row < (int64_t)hq * d)) ||
+      (hkv > 0 && (k_stride_row < (int64_t)hkv * d || k_out_stride_row < (int64_t)hkv * d)))
+    return set_error(HG_ERR_INVALID_ARGUMENT, "rope: a row stride is smaller than heads * head_dim");
+  RopeParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.k = k; p.q_out = q_out; p.k_out = k_out;
+  p.cos = cos_table; p.sin = sin_table;
+  p.positions = positions; p.positions_i64 = positions_i64;
+  p.rows = rows; p.hq = hq; p.hkv = hkv; p.d = d;
+  p.q_stride_row = q_stride_row; p.k_stride_row = k_stride_row;
+  p.q_out_stride_row = q_out_stride_row; p.k_out_stride_row = k_out_stride_row;
+  p.table_rows = table_rows;
+  return launch_rope(p, dtype, (cudaStream_t)stream);
+}
+
 }  // extern "C"

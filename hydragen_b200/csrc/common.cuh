@@ -189,4 +189,21 @@ int launch_allreduce_multimem(void* mc_ptr, void* out, const void* flags_dev, in
 int launch_kv_append(const void* k_new, const void* v_new, const void* positions, int positions_i64, void* k_cache,
                      void* v_cache, int b, int nq, int lk, int hkv, int d, int dtype, cudaStream_t s);
 
+
+struct RopeParams {
+  const void* q;
+  const void* k;
+  void* q_out;
+  void* k_out;
+  const void* cos;
+  const void* sin;
+  const void* positions;
+  int positions_i64;
+  int64_t rows;
+  int hq, hkv, d;
+  int64_t q_stride_row, k_stride_row, q_out_stride_row, k_out_stride_row;
+  int64_t table_rows;
+};
+int launch_rope(const RopeParams& p, int dtype, cudaStream_t s);
+
 }  // namespace hg

@@ -39,6 +39,7 @@ from torch import Tensor, nn
 from . import _lib
 from .attention import hydragen_attention, hydragen_attention_decode
 from .flash import flash_attention, flash_attention_seqlen
+from .rope import apply_rotary_pos_emb
 
 kv_append = _lib.kv_append  # (k_new, v_new, positions, k_cache, v_cache): module-level so tests can swap it
 
@@ -135,20 +136,21 @@ class HydragenLlamaRotaryEmbedding(nn.Module):
         emb = torch.cat((freqs, freqs), dim=-1)
         self.register_buffer("cos_cached", emb.cos(), persistent=False)
         self.register_buffer("sin_cached", emb.sin(), persistent=False)
+        self._cast: dict = {}  # (dtype, device) -> tables cast once
 
     def forward(self, x: Tensor, seq_len=None):
-        return self.cos_cached.to(dtype=x.dtype), self.sin_cached.to(dtype=x.dtype)
+        """The full tables in the activation dtype (hydragen/llama.py:47-55).  The reference casts them on
+        every call (once per layer per step); here the cast copy is made once per dtype and kept."""
+        return self.tables(x.dtype)
 
-    def rows(self, position_ids: Tensor, dtype: torch.dtype):
-        cos = self.cos_cached[position_ids].to(dtype).unsqueeze(2)  # [b, s, 1, d]
-        sin = self.sin_cached[position_ids].to(dtype).unsqueeze(2)
-        return cos, sin
-
-
-def _rope(x: Tensor, cos: Tensor, sin: Tensor) -> Tensor:
-    half = x.shape[-1] // 2
-    rot = torch.cat((-x[..., half:], x[..., :half]), dim=-1)
-    return x * cos + rot * sin
+    def tables(self, dtype: torch.dtype):
+        key = (dtype, self.cos_cached.device)
+        hit = self._cast.get(key)
+        if hit is None:
+            hit = (self.cos_cached.to(dtype=dtype).contiguous(), self.sin_cached.to(dtype=dtype).contiguous())
+            self._cast.clear()
+            self._cast[key] = hit
+        return hit
 
 
 def repeat_to_batch_size(tensors: Sequence[Tensor], target_batch_size: Optional[int] = None) -> List[Tensor]:
@@ -370,8 +372,9 @@ def hydragen_decode_on_caches(q: Tensor, k_new: Tensor, v_new: Tensor, positions
 class StepContext:
     """Per-forward quantities that depend only on position_ids; computed once, used by every layer."""
 
-    cos: Tensor  # [b, s, 1, d]
+    cos: Tensor  # the full RoPE tables [max_pos, d] in the activation dtype
     sin: Tensor
+    position_ids: Tensor  # [b, s] absolute positions (rows of the tables)
     unique_position_ids: Tensor  # [b, s] position inside the unique cache
     seq_lens: Optional[Tensor]  # decode: unique_position + 1, [b] int64
     host_lens: Optional[List[int]] = None  # shared prefill: valid lengths as Python ints
@@ -405,8 +408,9 @@ class HydragenLlamaAttention(nn.Module):
         q = self.q_proj(hidden_states).view(b, s, self.num_heads, self.head_dim)
         k = self.k_proj(hidden_states).view(b, s, self.num_key_value_heads, self.head_dim)
         v = self.v_proj(hidden_states).view(b, s, self.num_key_value_heads, self.head_dim)
-        q = _rope(q, ctx.cos, ctx.sin)  # absolute positions: shared K is stored already rotated
-        k = _rope(k, ctx.cos, ctx.sin)
+        # one launch (the reference: a gather + ten elementwise launches, hydragen/llama.py:494-501); in place on
+        # the fresh projection outputs.  Absolute positions: shared K is stored already rotated.
+        q, k = apply_rotary_pos_emb(q, k, ctx.cos, ctx.sin, ctx.position_ids, unsqueeze_dim=2, inplace=True)
         cache = self.kv_cache
 
         if self.disable_attention:
@@ -519,12 +523,12 @@ class HydragenLlamaModel(nn.Module):
     # -- forward -----------------------------------------------------------------------------------
     def make_context(self, position_ids: Tensor, dtype: torch.dtype, valid_lens: Optional[Tensor] = None) -> StepContext:
         cache = self._attn().kv_cache
-        cos, sin = self.rotary_emb.rows(position_ids, dtype)
+        cos, sin = self.rotary_emb.tables(dtype)
         if self.get_disable_hydragen():
             upos = position_ids
         else:
             upos = position_ids - cache.get_shared_len(position_ids.shape[0]).unsqueeze(-1)
-        ctx = StepContext(cos=cos, sin=sin, unique_position_ids=upos, seq_lens=None)
+        ctx = StepContext(cos=cos, sin=sin, position_ids=position_ids, unique_position_ids=upos, seq_lens=None)
         if self.mode == AttentionMode.DECODE:
             ctx.seq_lens = upos[:, -1] + 1
         elif self.mode == AttentionMode.SHARED_PREFILL:

@@ -208,6 +208,26 @@ int hg_decode_attn_fused(const void* q, const void* k_new, const void* v_new, co
 int hg_allreduce_multimem(void* mc_ptr, void* out, const void* flags_dev, int rank, int world,
                           int64_t nbytes, int dtype, int n_blocks, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Rotary position embedding of the new q and k rows in one launch ("next" row N2 of SURVEY.md 8f): the
+ * step right before the hot path.  Replaces apply_rotary_pos_emb as called at hydragen/llama.py:494-501
+ * (transformers 4.37.2: cos[position_ids].unsqueeze(2); x * cos + rotate_half(x) * sin for q and for k --
+ * a gather and ten elementwise launches per layer).  Half-split rotation: element i pairs with i + d/2.
+ * The result is bit-identical to that eager evaluation in the activation dtype (each product and the sum
+ * rounded to `dtype`, no FMA contraction).
+ *   q [rows, hq, d], k [rows, hkv, d]  heads dense, row strides q_stride_row / k_stride_row (elements) -- e.g.
+ *                      views of one fused qkv projection output; rows = b * s
+ *   q_out, k_out       same shapes, own row strides; may alias q / k (in place)
+ *   cos_table, sin_table [table_rows, d] contiguous, dtype `dtype` (the cached tables of
+ *                      HydragenLlamaRotaryEmbedding, hydragen/llama.py:47-55)
+ *   positions [rows]   absolute position of every row (int32 / int64), 0 <= positions[r] < table_rows
+ * d must be a multiple of 16 (16-bit dtypes) / 8 (fp32); hq or hkv may be 0.
+ */
+int hg_rope_qk(const void* q, const void* k, void* q_out, void* k_out, const void* cos_table,
+               const void* sin_table, const void* positions, int positions_i64, int64_t rows, int hq,
+               int hkv, int d, int64_t q_stride_row, int64_t k_stride_row, int64_t q_out_stride_row,
+               int64_t k_out_stride_row, int64_t table_rows, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,15 @@ What it restates (all citations are into /root/reference):
                                batching order "(n s)", LSE layout [b, nq, h], early return
                                when k is empty and there is one level).
 * ``concat_attention``         ground truth of tests/test_attention.py:132-178.
+* ``rotary_tables`` / ``apply_rotary_pos_emb``
+                               the step right before the path: RoPE as
+                               hydragen/llama.py:47-55, 494-501 calls it.  The arithmetic lives in
+                               transformers==4.37.2 (requirements.txt, NOT in tree): half-split
+                               rotation, tables cos/sin(cat(freqs, freqs)), inv_freq = base^(-2i/d),
+                               ``cos[position_ids].unsqueeze(dim)``.  Pinned against the installed
+                               transformers' own ``apply_rotary_pos_emb`` / ``rotate_half`` (same
+                               formula, gather done by the caller since v4.38):
+                               tests/golden/make_golden_rope.py -> tests/golden/rope_golden.npz.
 
 Pinning: the reference keeps NO golden vectors for this path and its
 attention entry points cannot execute without a GPU.  The oracle is pinned instead
@@ -58,6 +67,9 @@ __all__ = [
     "combine_lse_torch",
     "hydragen_attention",
     "hydragen_attention_nopad",
+    "rotary_tables",
+    "rotate_half",
+    "apply_rotary_pos_emb",
     "concat_attention",
 ]
 
@@ -370,3 +382,32 @@ def build_case(sizes, qheads: int, kvheads: int, dim: int, dtype=torch.float16, 
         q=q, k=k, v=v, shared_ks=shared_ks, shared_vs=shared_vs, shared_cu_seq_lens=shared_cu,
         shared_max_seq_lens=max_lens, use_varlens=use_varlens, seq_lens=seq_lens,
     )
+
+
+# ----------------------------------------------------------------------------------------------
+# RoPE (the step before the path)
+# ----------------------------------------------------------------------------------------------
+
+
+def rotary_tables(dim: int, max_position_embeddings: int, base: float = 10000.0, dtype=torch.float32):
+    """LlamaRotaryEmbedding of transformers 4.37.2 as imported at hydragen/llama.py:1-10 (pinned upstream, not in
+    tree): inv_freq = base^(-2i/d), emb = cat(freqs, freqs); HydragenLlamaRotaryEmbedding.forward
+    (hydragen/llama.py:47-55) returns the full tables cast to the activation dtype."""
+    inv_freq = 1.0 / (base ** (torch.arange(0, dim, 2, dtype=torch.float32) / dim))
+    t = torch.arange(max_position_embeddings, dtype=torch.float32)
+    emb = torch.cat((torch.outer(t, inv_freq),) * 2, dim=-1)
+    return emb.cos().to(dtype), emb.sin().to(dtype)
+
+
+def rotate_half(x: Tensor) -> Tensor:
+    half = x.shape[-1] // 2
+    return torch.cat((-x[..., half:], x[..., :half]), dim=-1)
+
+
+def apply_rotary_pos_emb(q: Tensor, k: Tensor, cos: Tensor, sin: Tensor, position_ids: Tensor, unsqueeze_dim: int = 2):
+    """The call at hydragen/llama.py:494-501: q [b, s, hq, d], k [b, s, hkv, d], cos/sin [max_pos, d] in the
+    activation dtype, position_ids [b, s] absolute positions.  Evaluated eagerly in the activation dtype,
+    operation by operation, exactly as transformers 4.37.2 does (the CUDA kernel reproduces the same bits)."""
+    c = cos[position_ids].unsqueeze(unsqueeze_dim)
+    s_ = sin[position_ids].unsqueeze(unsqueeze_dim)
+    return (q * c) + (rotate_half(q) * s_), (k * c) + (rotate_half(k) * s_)

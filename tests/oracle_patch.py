@@ -57,6 +57,11 @@ def hydragen_attention_decode(q, k_new, v_new, positions, k_cache, v_cache, shar
                               shared_max_seq_lens or [None] * n, use_varlens or [False] * n, seq_lens=seq_lens)
 
 
+def apply_rotary_pos_emb(q, k, cos, sin, position_ids, unsqueeze_dim=2, inplace=False):
+    """hydragen/llama.py:494-501 through the oracle's eager restatement (device-agnostic torch ops)."""
+    return O.apply_rotary_pos_emb(q, k, cos, sin, position_ids, unsqueeze_dim=unsqueeze_dim)
+
+
 def apply(monkeypatch):
     """Route every attention call of hydragen_b200.llama through the oracle."""
     import hydragen_b200.llama as L
@@ -66,3 +71,4 @@ def apply(monkeypatch):
     monkeypatch.setattr(L, "hydragen_attention", hydragen_attention)
     monkeypatch.setattr(L, "hydragen_attention_decode", hydragen_attention_decode)
     monkeypatch.setattr(L, "kv_append", kv_append)
+    monkeypatch.setattr(L, "apply_rotary_pos_emb", apply_rotary_pos_emb)

@@ -90,3 +90,20 @@ def test_early_return_without_unique_keys():
     out = O.hydragen_attention(**c)
     so, _ = O.flash_attention(c["q"].reshape(1, 3, 4, 64), c["shared_ks"][0], c["shared_vs"][0])
     assert (out - so.reshape(3, 1, 4, 64)).abs().max() < 1e-12
+
+
+def test_rope_oracle_matches_transformers_golden():
+    """oracle.apply_rotary_pos_emb / rotary_tables vs the outputs of transformers' own apply_rotary_pos_emb
+    (tests/golden/make_golden_rope.py) -- bit-exact in every dtype."""
+    import make_golden_rope as MR
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "rope_golden.npz"))
+    for name, b, s, hq, hkv, d, dtype, max_pos, seed in MR.CASES:
+        q, k, pos = MR.make_inputs(b, s, hq, hkv, d, dtype, max_pos, seed)
+        assert abs(MR.checksum(q, k, pos) - float(gold[name + "/checksum"])) < 1e-6
+        cos, sin = O.rotary_tables(d, max_pos, 10000.0, DT[dtype])
+        qe, ke = O.apply_rotary_pos_emb(q, k, cos, sin, pos, unsqueeze_dim=2)
+        for got, key in ((qe, "/q"), (ke, "/k")):
+            ref = torch.from_numpy(gold[name + key])
+            got = got.contiguous().view(torch.int16) if DT[dtype] != torch.float32 else got
+            assert torch.equal(got, ref), f"{name}{key}"

@@ -31,7 +31,7 @@ def _patch_oracle():
     import hydragen_b200.llama as L
     import oracle_patch as P
 
-    for name in ("flash_attention", "flash_attention_seqlen", "hydragen_attention", "hydragen_attention_decode", "kv_append"):
+    for name in ("flash_attention", "flash_attention_seqlen", "hydragen_attention", "hydragen_attention_decode", "kv_append", "apply_rotary_pos_emb"):
         setattr(L, name, getattr(P, name))
 
 
