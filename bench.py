@@ -357,9 +357,26 @@ def run_ours(a):
         torch.cuda.synchronize()
         return t0.elapsed_time(t1) * 1e3 / (reps * L)  # us per launch
 
+    # the step right before the path: RoPE of the new q / k rows, one launch per layer, in place
+    from hydragen_b200.rope import apply_rotary_pos_emb
+
+    max_pos = 4096
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2, device=dev, dtype=torch.float32) / D))
+    ang = torch.outer(torch.arange(max_pos, device=dev, dtype=torch.float32), inv)
+    cos_t, sin_t = torch.cat((ang, ang), -1).cos().to(dt), torch.cat((ang, ang), -1).sin().to(dt)
+    abs_pos = torch.full((B, 1), a.prefix_len + a.suffix_len - 1, device=dev, dtype=torch.int64)
+    rq = [t.clone() for t in qs]
+    rk = [t.clone() for t in kn]
+
+    def only_rope():
+        for i in range(L):
+            apply_rotary_pos_emb(rq[i], rk[i], cos_t, sin_t, abs_pos, inplace=True)
+
     pre_t = time_kernel_graph(only_prefix)
     suf_t = time_kernel_graph(only_suffix)
-    _log(f"per-kernel timing done: prefix {pre_t:.1f} us, suffix {suf_t:.1f} us")
+    rope_t = time_kernel_graph(only_rope)
+    del rq, rk
+    _log(f"per-kernel timing done: prefix {pre_t:.1f} us, suffix {suf_t:.1f} us, rope {rope_t:.1f} us")
     pre_flops = 4.0 * B * H * a.prefix_len * D
     esz = 2
     # new K,V rows read + appended, older K,V rows read, q + prefix partial + out, 2 LSE rows
@@ -370,6 +387,10 @@ def run_ours(a):
     roofline_suffix = {"kernel": "decode_slot_kernel (kv append + suffix + combine)", "bound": "hbm", "achieved": suf_bytes / suf_t / 1e3, "peak": hbm_peak,
                        "unit": "GB/s", "frac": suf_bytes / suf_t / 1e3 / hbm_peak, "traffic": None, "us_per_launch": suf_t,
                        "algorithmic_bytes_per_launch": suf_bytes, "peak_source": peak_src}
+    rope_bytes = 2.0 * B * (H + HKV) * D * esz  # q and k rows read and written once (table rows stay in cache)
+    roofline_rope = {"kernel": "rope_qk_kernel (next row N2: RoPE of the new q/k rows, not part of the timed step)", "bound": "hbm",
+                     "achieved": rope_bytes / rope_t / 1e3, "peak": hbm_peak, "unit": "GB/s", "frac": rope_bytes / rope_t / 1e3 / hbm_peak,
+                     "traffic": None, "us_per_launch": rope_t, "algorithmic_bytes_per_launch": rope_bytes, "peak_source": peak_src}
     prof = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch read from the committed ncu --set full capture
     if os.path.exists(prof):
         try:
@@ -446,7 +467,7 @@ def run_ours(a):
                        "parallelism": (f"tp{world} (head axis, 1 all-reduce of [B,{hidden}] bf16 per layer: " + ("hg_allreduce_multimem NVLS kernel" if nvls is not None else "NCCL") + ")") if world > 1 else "single GPU",
                        "l2": f"inputs larger than L2: {L} layers x distinct caches cycle {L * (2 * a.prefix_len * HKV * D * 2 + 4 * B * H * D * 2) / 2**20:.0f}+ MiB per step through a 126 MB L2",
                        "cuda_graph": graph is not None},
-            "roofline": roofline, "roofline_suffix": roofline_suffix, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "roofline_suffix": roofline_suffix, "roofline_rope": roofline_rope, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
         }
         if full_model is not None:
