@@ -46,6 +46,11 @@ SYMBOLS = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
          c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_int, c_void_p],
     ),
+    "hg_causal_attn_fwd": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64,
+         c_float, c_int, c_void_p],
+    ),
     "hg_prefix_suggest_splits": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "hg_decode_attn_fused": (
         c_int,
@@ -191,6 +196,14 @@ def prefix_attn_fwd(q, k, v, out, lse, n_groups, q_per_group, n_k_rows, k_len, c
                 _ptr(cu_seqlens_k), max_k_len, hq, hkv, d, q_stride_row, kv_stride_row, float(sm_scale),
                 dtype_code(q.dtype), kv_splits, _stream(q))
     _check(rc, "hg_prefix_attn_fwd")
+
+
+def causal_attn_fwd(q, k, v, out, lse, b, sq, sk, hq, hkv, d, q_stride_row, kv_stride_row, sm_scale) -> None:
+    ensure_init(q.device)
+    with torch.cuda.device(q.device):
+        rc = load().hg_causal_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), b, sq, sk, hq, hkv, d, q_stride_row,
+                                       kv_stride_row, float(sm_scale), dtype_code(q.dtype), _stream(q))
+    _check(rc, "hg_causal_attn_fwd")
 
 
 def prefix_suggest_splits(device, n_groups: int, q_per_group: int, hq: int, max_k_len: int, max_splits: int) -> int:

@@ -222,6 +222,30 @@ int hg_prefix_attn_split_fwd(const void* q, const void* k, const void* v, void* 
   return launch_prefix(p, dtype, (cudaStream_t)stream);
 }
 
+int hg_causal_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int b, int sq, int sk, int hq, int hkv,
+                       int d, int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype, void* stream) {
+  if (!g_info.ready) return set_error(HG_ERR_NOT_INITIALIZED, "causal_attn: hg_init() has not been called");
+  if (b < 0 || sq < 0 || sk < 0 || hq < 1 || hkv < 1)
+    return set_error(HG_ERR_INVALID_ARGUMENT, "causal_attn: bad sizes b=%d sq=%d sk=%d hq=%d hkv=%d", b, sq, sk, hq, hkv);
+  if (hq % hkv != 0) return set_error(HG_ERR_INVALID_ARGUMENT, "causal_attn: hq (%d) must be a multiple of hkv (%d)", hq, hkv);
+  if (sk < sq) return set_error(HG_ERR_UNSUPPORTED, "causal_attn: sk (%d) < sq (%d): rows without any visible key are not supported", sk, sq);
+  if (b > 0 && sq > 0 && (q == nullptr || out == nullptr || k == nullptr || v == nullptr))
+    return set_error(HG_ERR_INVALID_ARGUMENT, "causal_attn: null tensor pointer");
+  if ((int64_t)b * sq > 0x7fffffffLL || (int64_t)b * sk > 0x7fffffffLL)
+    return set_error(HG_ERR_UNSUPPORTED, "causal_attn: row counts must fit int32");
+  PrefixParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.k = k; p.v = v; p.out = out; p.lse = lse;
+  p.n_groups = b; p.q_per_group = sq;
+  p.n_k_rows = (int64_t)b * sk; p.k_len = sk; p.max_k_len = sk;
+  p.hq = hq; p.hkv = hkv; p.d = d;
+  p.q_stride_row = q_stride_row; p.kv_stride_row = kv_stride_row;
+  p.scale_log2 = sm_scale * kLog2e;
+  p.kv_splits = 1;
+  p.causal = 1;
+  return launch_prefix(p, dtype, (cudaStream_t)stream);
+}
+
 int hg_allreduce_multimem(void* mc_ptr, void* out, const void* flags_dev, int rank, int world, int64_t nbytes, int dtype,
                           int n_blocks, void* stream) {
   if (!valid_dtype(dtype)) return set_error(HG_ERR_INVALID_ARGUMENT, "allreduce: unknown dtype %d", dtype);

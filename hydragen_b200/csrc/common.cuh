@@ -179,6 +179,7 @@ struct PrefixParams {
   int64_t q_stride_row, kv_stride_row;
   float scale_log2;
   int kv_splits;  // >= 1; out / lse then hold kv_splits partial results back to back
+  int causal;     // bottom-right aligned causal mask inside every group (prefill): row r sees keys <= r + (k_len - q_per_group)
 };
 int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s);
 int suggest_prefix_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits);

@@ -317,7 +317,7 @@ struct Barriers {
 
 }  // namespace
 
-#ifdef HG_PREFIX_TRACE
+#if defined(HG_PREFIX_TRACE) && !defined(HG_PREFIX_TU_CAUSAL)
 // Development aid (never compiled into the shipped library): clock64 stamps of CTA (0,0).
 // Layout: [role][block j][slot]; role 0 = MMA thread, 1 = softmax warp of tile A, 2 = tile B.
 __device__ long long g_trace[3 * 64 * 8];
@@ -331,7 +331,9 @@ __device__ long long g_trace[3 * 64 * 8];
   } while (0)
 #endif
 
-template <typename T, int D>
+// kCausal: bottom-right aligned causal mask inside every group (the prefill form, flash_attention(causal=True) of
+// hydragen/flash.py:284-306); a separate instantiation so that the decode-path kernel is exactly the unmasked code.
+template <typename T, int D, bool kCausal>
 __global__ void __launch_bounds__(kThreads, 1)
     prefix_attn_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
@@ -351,7 +353,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   // blockIdx.x = (group, m-tile, kv split): the splits of one tile sit next to each other
   const int split = blockIdx.x % kv_splits;
   const int tile = blockIdx.x / kv_splits, head = blockIdx.y;
-  const int grp = tile / tiles_per_group, mt = tile % tiles_per_group;
+  const int grp = tile / tiles_per_group;
+  // causal: later row tiles see more keys -- launch them first
+  const int mt = kCausal ? tiles_per_group - 1 - tile % tiles_per_group : tile % tiles_per_group;
   const int kvh = head / (hq / hkv);
   const int q_row0 = grp * q_per_group + mt * (kTiles * BLOCK_M);
   const int rows_left = q_per_group - mt * (kTiles * BLOCK_M);  // > 0
@@ -373,6 +377,14 @@ __global__ void __launch_bounds__(kThreads, 1)
     k_len = max(0, min(k_len - first, bps * BLOCK_N));
     out += (int64_t)split * n_q_rows * hq * D;
     if (lse != nullptr) lse += (int64_t)split * n_q_rows * hq;
+  }
+  // causal (bottom-right aligned, flash-attn >= 2.1): row r of the group sees keys j <= r + causal_off.  The CTA
+  // streams only the keys its last row can see; the rows above it are masked per element in the diagonal blocks.
+  int causal_off = 0;
+  if (kCausal) {
+    causal_off = k_len - q_per_group;  // >= 0 (checked by the launcher)
+    const int last_row = min(q_per_group, (mt + 1) * (kTiles * BLOCK_M)) - 1;
+    k_len = min(k_len, last_row + causal_off + 1);
   }
   const int n_blocks = (k_len + BLOCK_N - 1) / BLOCK_N;
 
@@ -563,8 +575,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       // register arrays alternate between "being exponentiated" and "being fetched".
       uint32_t sa[BLOCK_N], sb[BLOCK_N];
       float m_blk;
+      // first key (group-relative) this thread's row may NOT see; tile_lim: the same for the tile's first row
+      const int row_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + row + causal_off + 1 : 0x7fffffff;
+      const int tile_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + causal_off + 1 : 0x7fffffff;
+      const bool ragged = (k_len % BLOCK_N) != 0;
+      // block jb holds a key some row of this tile must not see (warp-uniform)
+      auto needs_mask = [&](int jb) { return (ragged && jb + 1 == n_blocks) || (jb + 1) * BLOCK_N > tile_end; };
       auto mask_tail = [&](uint32_t(&x)[BLOCK_N], int j) {
-        const int rem = k_len - j * BLOCK_N;
+        const int rem = min(k_len, row_end) - j * BLOCK_N;
 #pragma unroll
         for (int c = 0; c < BLOCK_N; ++c)
           if (c >= rem) x[c] = 0xff800000u;  // -inf
@@ -691,15 +709,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         HG_TMEM_LD32(s_addr + 0, sa, 0);
         HG_TMEM_LD32(s_addr + 32, sa, 32);
         tmem_wait_ld();
-        if (k_len < BLOCK_N) mask_tail(sa, 0);
+        if (needs_mask(0)) mask_tail(sa, 0);
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int g = 0; g < 8; ++g) max8(mx, sa, g);
         m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       }
-      const bool ragged = (k_len % BLOCK_N) != 0;
       for (int j = 0; j < n_blocks; ++j) {
-        const bool last = j + 1 == n_blocks, mask_next = ragged && (j + 2 == n_blocks);
+        const bool last = j + 1 == n_blocks, mask_next = !last && needs_mask(j + 1);
         if ((j & 1) == 0) {
           if (last) body(j, sa, sb, std::false_type{}, std::false_type{});
           else if (mask_next) body(j, sa, sb, std::true_type{}, std::true_type{});
@@ -801,7 +818,7 @@ static int make_tmap(CUtensorMap* map, const void* base, int dtype, uint64_t row
   return HG_OK;
 }
 
-template <typename T, int D>
+template <typename T, int D, bool kCausal>
 static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) {
   using L = SmemLayout<D>;
   const int64_t n_q_rows = (int64_t)p.n_groups * p.q_per_group;
@@ -815,7 +832,7 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   const int smem_bytes = L::kTotal + 1024;
   static bool attr_set = false;  // per instantiation; idempotent, racing threads set the same value
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(prefix_attn_sm100_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(prefix_attn_sm100_kernel<T, D, kCausal>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return set_error(HG_ERR_CUDA, "prefix: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -830,7 +847,7 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, prefix_attn_sm100_kernel<T, D>, tq, tk, tv, to, (T*)p.out, p.lse, p.cu_seqlens_k, p.q_per_group,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, prefix_attn_sm100_kernel<T, D, kCausal>, tq, tk, tv, to, (T*)p.out, p.lse, p.cu_seqlens_k, p.q_per_group,
                                      tiles_per_group, p.k_len, p.hq, p.hkv, p.scale_log2, splits, (int)n_q_rows);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -839,6 +856,7 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   return check_launch("prefix_attn_sm100");
 }
 
+#ifndef HG_PREFIX_TU_CAUSAL
 #ifdef HG_PREFIX_TRACE
 extern "C" int hg_debug_read_trace(long long* host_buf, int n) {
   cudaDeviceSynchronize();
@@ -859,6 +877,8 @@ int suggest_prefix_splits(int n_groups, int q_per_group, int hq, int max_k_len, 
   return s < 1 ? 1 : s;
 }
 
+int launch_prefix_causal(const PrefixParams& p, int dtype, cudaStream_t s);  // prefix_sm100_causal.cu
+
 int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
   if (p.n_groups == 0 || p.q_per_group == 0) return HG_OK;
   if (dtype != HG_F16 && dtype != HG_BF16)
@@ -868,14 +888,31 @@ int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
       reinterpret_cast<uintptr_t>(p.out) % 16 != 0)
     return set_error(HG_ERR_UNSUPPORTED, "prefix: TMA needs 16-byte aligned bases and row strides");
   if (p.hq > 65535) return set_error(HG_ERR_UNSUPPORTED, "prefix: hq > 65535");
+  if (p.causal) {
+    if (p.cu_seqlens_k != nullptr || p.kv_splits > 1 || p.k_len < p.q_per_group)
+      return set_error(HG_ERR_UNSUPPORTED, "prefix: the causal form takes uniform groups with k_len >= q rows per group and no kv split");
+    return launch_prefix_causal(p, dtype, s);
+  }
   if (dtype == HG_BF16) {
-    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64>(p, dtype, s);
+    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, false>(p, dtype, s);
   } else {
-    if (p.d == 128) return launch_prefix_inst<__half, 128>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__half, 64>(p, dtype, s);
+    if (p.d == 128) return launch_prefix_inst<__half, 128, false>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__half, 64, false>(p, dtype, s);
   }
   return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
 }
+#else   // HG_PREFIX_TU_CAUSAL: the second translation unit holds the causal instantiations (compiled in parallel)
+int launch_prefix_causal(const PrefixParams& p, int dtype, cudaStream_t s) {
+  if (dtype == HG_BF16) {
+    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, true>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, true>(p, dtype, s);
+  } else {
+    if (p.d == 128) return launch_prefix_inst<__half, 128, true>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__half, 64, true>(p, dtype, s);
+  }
+  return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
+}
+#endif
 
 }  // namespace hg

@@ -5,8 +5,8 @@ hand-written sm_100a kernels behind the C ABI.  No flash-attn, no Triton, no CPU
 =====================================  =======================================================
 reference (hydragen/flash.py)          here
 =====================================  =======================================================
-``flash_attention`` :284-306           tcgen05 prefix kernel (non-causal, 16-bit, d in {64,128});
-  (flash-attn _flash_attn_forward)     row-wise kernel otherwise (causal / fp32)
+``flash_attention`` :284-306           tcgen05 prefix kernel (16-bit, d in {64,128}; causal = its masked
+  (flash-attn _flash_attn_forward)     instantiation, sk >= sq); row-wise kernel otherwise (fp32, tiny chunks)
 ``flash_attention_varlen`` :309-351    tcgen05 prefix kernel with a device ``cu_seqlens_k`` table
 ``flash_attention_seqlen`` :163-281    row-wise kernel (one launch instead of cast + split-K +
   (+ Triton kernels, pick_split_k)     reduce); warps-per-sequence chosen from the cache length
@@ -30,6 +30,11 @@ from . import _lib
 
 _TC_DTYPES = (torch.float16, torch.bfloat16)
 _TC_HEAD_DIMS = (64, 128)
+
+
+def _causal_backend() -> str:
+    """'auto' (default: tcgen05 when the shape allows), 'tcgen05' or 'rowwise' -- test hook, read per call."""
+    return os.environ.get("HYDRAGEN_B200_CAUSAL_BACKEND", "auto")
 
 
 def _prefix_backend() -> str:
@@ -170,6 +175,26 @@ def flash_attention(q: Tensor, k: Tensor, v: Tensor, causal: bool = False) -> Tu
     b, sq, hq, d = q.shape
     if not causal:
         out, lse = prefix_attention_grouped(q, k, v, n_groups=b)
+        return out, lse.permute(0, 2, 1)
+    sk = k.shape[1]
+    backend = _causal_backend()
+    # prefill chunks go to the tensor cores; tiny ones (a few rows: launch-bound either way) and shapes the tcgen05
+    # kernel does not take (fp32, other head dims, sk < sq) stay on the CUDA-core kernel
+    use_tc = q.dtype in _TC_DTYPES and d in _TC_HEAD_DIMS and sk >= sq and backend != "rowwise" and (backend == "tcgen05" or sq >= 16)
+    if backend == "tcgen05" and not use_tc:
+        raise ValueError(f"tcgen05 causal kernel does not take dtype {q.dtype} / head_dim {d} / sq {sq} > sk {sk}")
+    if use_tc:
+        q_rs = _rows_view(q)
+        if q_rs is None:
+            q = q.contiguous()
+            q_rs = hq * d
+        kv_rs = _rows_view(k)
+        if kv_rs is None or _rows_view(v) != kv_rs:
+            k, v = k.contiguous(), v.contiguous()
+            kv_rs = k.shape[2] * d
+        out = torch.empty((b, sq, hq, d), device=q.device, dtype=q.dtype)
+        lse = torch.empty((b, sq, hq), device=q.device, dtype=torch.float32)
+        _lib.causal_attn_fwd(q, k, v, out, lse, b, sq, sk, hq, k.shape[2], d, q_rs, kv_rs, d**-0.5)
         return out, lse.permute(0, 2, 1)
     out, lse = _rowwise(q, k, v, None, causal=True)
     return out, lse.permute(0, 2, 1)

@@ -157,6 +157,20 @@ int hg_prefix_attn_split_fwd(const void* q, const void* k, const void* v, void* 
 int hg_prefix_suggest_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits);
 
 /* ---------------------------------------------------------------------------------------
+ * Causal self-attention of a prefill chunk on the tensor cores: the same tcgen05 kernel with a bottom-right
+ * aligned causal mask (row i of a sequence sees keys j <= i + (sk - sq); flash-attn >= 2.1) -- only the key
+ * blocks a row tile can see are streamed, the mask is applied in the diagonal blocks.
+ * Replaces flash_attention(q, k, v, causal=True) (hydragen/flash.py:284-306) as called by the prefill branches
+ * (hydragen/llama.py:509, 537-542, 546).
+ *   q [b * sq, hq, d] row stride q_stride_row;  k, v [b * sk, hkv, d] row stride kv_stride_row (sequence i owns
+ *   rows [i*sq, (i+1)*sq) / [i*sk, (i+1)*sk));  out [b * sq, hq, d] contiguous;  lse [b * sq, hq] fp32 or NULL.
+ * dtype HG_F16 / HG_BF16, d 64 or 128, sk >= sq (no row without a visible key).
+ */
+int hg_causal_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int b, int sq,
+                       int sk, int hq, int hkv, int d, int64_t q_stride_row, int64_t kv_stride_row,
+                       float sm_scale, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * KV-cache append for one decode step ("next" row N1 of SURVEY.md 8f): writes the new key and
  * value row of every sequence at its own position.  Replaces the two scatter_ calls with a
  * fully expanded int64 index in PerLayerKVCache.update_per_completion_kvs
