@@ -38,6 +38,7 @@
 // 7B config), with the MUFU exp2 rate (16/clk/SM == the 128x128x128 MMA rate) the co-limiter.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -49,11 +50,15 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 64;   // keys per block: S_t block = 64 TMEM columns, double buffered
 constexpr int kTiles = 2;  // Q tiles per CTA (ping-pong)
-constexpr int kThreads = 384;
+constexpr int kThreads = 384;       // base: TMA / MMA warpgroup + one softmax warpgroup per tile
+constexpr int kThreadsSplit = 640;  // split-column softmax: two softmax warpgroups per tile
 constexpr uint32_t kTmemCols = 512;
 __host__ __device__ constexpr uint32_t tmem_s(int t, int b) { return (uint32_t)t * 128u + (uint32_t)b * 64u; }  // S_t buffer b (P aliases its first 32 columns)
 __host__ __device__ constexpr uint32_t tmem_o(int t) { return 256u + (uint32_t)t * 128u; }                       // O_t
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+#ifndef HG_PREFIX_SPLIT_DEFAULT
+#define HG_PREFIX_SPLIT_DEFAULT false  // softmax organisation used when HYDRAGEN_B200_PREFIX_SOFTMAX is not set
+#endif
 #ifndef HG_PREFIX_EMU_EVERY
 #define HG_PREFIX_EMU_EVERY 0
 #endif
@@ -286,6 +291,9 @@ template <int ID, int THREADS>
 __device__ __forceinline__ void named_bar_sync() {
   asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(THREADS) : "memory");
 }
+__device__ __forceinline__ void named_bar_sync_rt(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 constexpr int kStages = 4;  // K/V ring depth
 
@@ -303,7 +311,8 @@ struct SmemLayout {
   static constexpr int kQ = 0;                              // 2 tiles (A, B)
   static constexpr int kKV = kQTileBytes * kTiles;
   static constexpr int kBars = kKV + kStageBytes * kStages;
-  static constexpr int kTotal = kBars + 512;
+  static constexpr int kXchg = kBars + 512;  // split-column softmax: fp32 [parity][tile][half][row] row-max / row-sum exchange
+  static constexpr int kTotal = kXchg + 2 * kTiles * 2 * BLOCK_M * 4;
 };
 
 struct Barriers {
@@ -317,7 +326,7 @@ struct Barriers {
 
 }  // namespace
 
-#if defined(HG_PREFIX_TRACE) && !defined(HG_PREFIX_TU_CAUSAL)
+#if defined(HG_PREFIX_TRACE) && !defined(HG_PREFIX_TU_CAUSAL) && !defined(HG_PREFIX_TU_SPLIT)
 // Development aid (never compiled into the shipped library): clock64 stamps of CTA (0,0).
 // Layout: [role][block j][slot]; role 0 = MMA thread, 1 = softmax warp of tile A, 2 = tile B.
 __device__ long long g_trace[3 * 64 * 8];
@@ -333,8 +342,13 @@ __device__ long long g_trace[3 * 64 * 8];
 
 // kCausal: bottom-right aligned causal mask inside every group (the prefill form, flash_attention(causal=True) of
 // hydragen/flash.py:284-306); a separate instantiation so that the decode-path kernel is exactly the unmasked code.
-template <typename T, int D, bool kCausal>
-__global__ void __launch_bounds__(kThreads, 1)
+//
+// kSplit: softmax organisation.  0 = one warpgroup per tile (thread = one row x 64 keys of a block, software
+// pipelined).  1 = TWO warpgroups per tile, each thread one row x 32 keys: four softmax warps per SM sub-partition
+// instead of two hide each other's TMEM / MUFU / barrier latencies (r01e: the two-warp form keeps the MUFU unit
+// only ~55 % busy); the two half-row maxima meet through shared memory and a 64-thread named barrier per block.
+template <typename T, int D, bool kCausal, int kSplit>
+__global__ void __launch_bounds__(kSplit ? kThreadsSplit : kThreads, 1)
     prefix_attn_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
                              T* __restrict__ out, float* __restrict__ lse, const int32_t* __restrict__ cu_seqlens_k,
@@ -390,12 +404,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (n_blocks == 0) {  // empty prefix: out = 0, lse = -inf (uniform branch for the whole CTA)
     const int rows = min(kTiles * BLOCK_M, rows_left);
-    for (int idx = threadIdx.x; idx < rows * (D / 8); idx += kThreads) {
+    for (int idx = threadIdx.x; idx < rows * (D / 8); idx += blockDim.x) {
       const int r = idx / (D / 8), c = idx % (D / 8);
       st_v4(out + ((int64_t)(q_row0 + r) * hq + head) * D + c * 8, make_uint4(0, 0, 0, 0));
     }
     if (lse != nullptr)
-      for (int r = threadIdx.x; r < rows; r += kThreads) lse[(int64_t)(q_row0 + r) * hq + head] = -INFINITY;
+      for (int r = threadIdx.x; r < rows; r += blockDim.x) lse[(int64_t)(q_row0 + r) * hq + head] = -INFINITY;
     return;
   }
 
@@ -413,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&bars->o_full[i], 1);
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bars->s_full[i][b], 1);
-        mbar_init(&bars->p_full[i][b], BLOCK_M);
+        mbar_init(&bars->p_full[i][b], BLOCK_M * (kSplit ? 2 : 1));
       }
     }
     for (int i = 0; i < kStages; ++i) {
@@ -445,8 +459,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   // Register budget (setmaxnreg must sit inside the role branch it applies to): the producer
   // warpgroup gives registers back, the two softmax warpgroups (128 live fp32 scores per thread)
   // take them: 128 x 88 + 256 x 208 <= 64K.
+  // (split-column form: 640 threads x 96 at launch -> 128 x 64 + 512 x 104.)
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if constexpr (kSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 0) {
     // =============================== TMA producer ===========================================
     if (elect_one()) {
@@ -553,6 +569,164 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   }
+  } else if constexpr (kSplit) {
+    // =============================== softmax, split-column form ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int sw = warp - 4;          // 0 .. 15
+    const int t = sw >> 3;            // tile owned by this pair of warpgroups
+    const int half = (sw >> 2) & 1;   // which 32 keys of every 64-key block (and which D/2 columns of O)
+    const int rows_valid = min(BLOCK_M, rows_left - t * BLOCK_M);
+    if (rows_valid > 0) {
+      constexpr int DH = D / 2;
+      const int wq = warp & 3;        // == sw % 4: the TMEM lane quarter this warp may access
+      const int row = wq * 32 + lane;
+      const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+      const uint32_t o_addr = tmem + lane_base + tmem_o(t) + (uint32_t)(half * DH);
+      float* xchg = reinterpret_cast<float*>(smem + L::kXchg);
+      const int pair_bar = 1 + t * 4 + wq;  // the two warps that own the same 32 rows (named barriers 1..8)
+      float m_used = -INFINITY, l = 0.f;
+      const int row_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + row + causal_off + 1 : 0x7fffffff;
+      const int tile_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + causal_off + 1 : 0x7fffffff;
+      const bool ragged = (k_len % BLOCK_N) != 0;
+      // value of the partner warp (same rows, other key half) for this thread's row; double buffered by parity
+      auto exchange = [&](int parity, float mine) {
+        float* slot = xchg + ((parity * kTiles + t) * 2) * BLOCK_M;
+        slot[half * BLOCK_M + row] = mine;
+        tc_fence_before();
+        named_bar_sync_rt(pair_bar, 64);
+        tc_fence_after();
+        return slot[(half ^ 1) * BLOCK_M + row];
+      };
+      for (int j = 0; j < n_blocks; ++j) {
+        const int b = j & 1;
+        const uint32_t s_addr = tmem + lane_base + tmem_s(t, b);
+        mbar_wait(&bars->s_full[t][b], (j >> 1) & 1);
+        tc_fence_after();
+        uint32_t sc[32];
+        HG_TMEM_LD32(s_addr + half * 32, sc, 0);
+        tmem_wait_ld();
+        if ((ragged && j + 1 == n_blocks) || (j + 1) * BLOCK_N > tile_end) {  // warp-uniform
+          const int rem = min(k_len, row_end) - j * BLOCK_N - half * 32;
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c >= rem) sc[c] = 0xff800000u;  // -inf
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(sc[c + 0]), __uint_as_float(sc[c + 1])));
+          mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(sc[c + 2]), __uint_as_float(sc[c + 3])));
+          mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(sc[c + 4]), __uint_as_float(sc[c + 5])));
+          mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(sc[c + 6]), __uint_as_float(sc[c + 7])));
+        }
+        const float m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        // Both warps of the pair hold their scores in registers once they pass the barrier inside exchange():
+        // only then may either of them overwrite the S buffer with its half of P.
+        const float m_blk = fmaxf(m_half, exchange(b, m_half));
+        const float m_new = fmaxf(m_used, m_blk);
+        if (j == 0) {
+          m_used = m_new;
+        } else {
+          const bool need = (m_new - m_used) * scale_log2 > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {  // the partner warp sees the same rows and takes the same branch
+            mbar_wait(&bars->pv_done[t], (j - 1) & 1);
+            tc_fence_after();
+            const float alpha = need ? fast_exp2((m_used - m_new) * scale_log2) : 1.f;
+            if (need) {
+              m_used = m_new;
+              l *= alpha;
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < DH; c0 += 32) {
+              uint32_t o[32];
+              HG_TMEM_LD32(o_addr + c0, o, 0);
+              tmem_wait_ld();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+              HG_TMEM_ST32(o_addr + c0, o, 0);
+            }
+          }
+        }
+        const float neg_mc = -m_used * scale_log2;
+        const uint64_t scale2 = pack_f2(scale_log2, scale_log2), neg2 = pack_f2(neg_mc, neg_mc);
+        uint64_t ps2[2] = {0ull, 0ull};
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float x0, x1;
+          unpack_f2(ffma2(pack_f2(__uint_as_float(sc[c]), __uint_as_float(sc[c + 1])), scale2, neg2), x0, x1);
+          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+          ps2[(c >> 1) & 1] = fadd2(ps2[(c >> 1) & 1], pack_f2(p0, p1));
+          pk[c >> 1] = pack2<T>(p0, p1);
+        }
+        HG_TMEM_ST16(s_addr + half * 16, pk, 0);  // P_t(j): keys [half*32, half*32+32) -> columns [half*16, half*16+16)
+        {
+          float a0, a1;
+          unpack_f2(fadd2(ps2[0], ps2[1]), a0, a1);
+          l += a0 + a1;
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bars->p_full[t][b]);
+      }
+
+      // ---- epilogue: this warp owns columns [half*DH, half*DH + DH) of its 32 rows of O_t ----
+      mbar_wait(&bars->o_full[t], 0);
+      tc_fence_after();
+      l += exchange(n_blocks & 1, l);  // row sum of both key halves
+      const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+      const int tile_row0 = q_row0 + t * BLOCK_M;
+      if (rows_valid == BLOCK_M) {
+        uint8_t* stage = smem + L::kQ + t * L::kQTileBytes;
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 32) {
+          uint32_t o[32];
+          HG_TMEM_LD32(o_addr + c0, o, 0);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            uint4 w;
+            w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+            w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+            w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+            w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+            const int chunk = (half * DH + c0 + c) >> 3;  // 16-byte chunk of the row
+            uint8_t* dst = stage + (chunk >> 3) * L::kQHalfBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = w;
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync_rt(9 + t, 2 * BLOCK_M);  // the eight warps of this tile
+        if (half == 0 && wq == 0 && lane == 0) {
+#pragma unroll
+          for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&tmap_o, stage + h * L::kQHalfBytes, head * D + h * 64, split * n_q_rows + tile_row0);
+          bulk_commit_and_wait();
+        }
+      } else {
+        const bool row_ok = row < rows_valid;
+        T* orow = out + ((int64_t)(tile_row0 + row) * hq + head) * D + half * DH;
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 32) {
+          uint32_t o[32];
+          HG_TMEM_LD32(o_addr + c0, o, 0);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+              uint4 w;
+              w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+              w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+              w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+              w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+              st_v4(orow + c0 + c, w);
+            }
+          }
+        }
+      }
+      if (half == 0 && row < rows_valid && lse != nullptr)
+        lse[(int64_t)(tile_row0 + row) * hq + head] = (l > 0.f) ? (m_used * scale_log2 + fast_log2(l)) * kLn2 : -INFINITY;
+      tc_fence_before();
+    }
   } else {
     // =============================== softmax / correction / epilogue ==========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
@@ -818,7 +992,7 @@ static int make_tmap(CUtensorMap* map, const void* base, int dtype, uint64_t row
   return HG_OK;
 }
 
-template <typename T, int D, bool kCausal>
+template <typename T, int D, bool kCausal, int kSplit>
 static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) {
   using L = SmemLayout<D>;
   const int64_t n_q_rows = (int64_t)p.n_groups * p.q_per_group;
@@ -832,14 +1006,14 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   const int smem_bytes = L::kTotal + 1024;
   static bool attr_set = false;  // per instantiation; idempotent, racing threads set the same value
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(prefix_attn_sm100_kernel<T, D, kCausal>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(prefix_attn_sm100_kernel<T, D, kCausal, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return set_error(HG_ERR_CUDA, "prefix: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int tiles_per_group = (p.q_per_group + kTiles * BLOCK_M - 1) / (kTiles * BLOCK_M);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(p.n_groups * tiles_per_group * splits), (unsigned)p.hq, 1);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kSplit ? kThreadsSplit : kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -847,7 +1021,7 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, prefix_attn_sm100_kernel<T, D, kCausal>, tq, tk, tv, to, (T*)p.out, p.lse, p.cu_seqlens_k, p.q_per_group,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, prefix_attn_sm100_kernel<T, D, kCausal, kSplit>, tq, tk, tv, to, (T*)p.out, p.lse, p.cu_seqlens_k, p.q_per_group,
                                      tiles_per_group, p.k_len, p.hq, p.hkv, p.scale_log2, splits, (int)n_q_rows);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -856,7 +1030,7 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   return check_launch("prefix_attn_sm100");
 }
 
-#ifndef HG_PREFIX_TU_CAUSAL
+#if !defined(HG_PREFIX_TU_CAUSAL) && !defined(HG_PREFIX_TU_SPLIT)
 #ifdef HG_PREFIX_TRACE
 extern "C" int hg_debug_read_trace(long long* host_buf, int n) {
   cudaDeviceSynchronize();
@@ -878,6 +1052,16 @@ int suggest_prefix_splits(int n_groups, int q_per_group, int hq, int max_k_len, 
 }
 
 int launch_prefix_causal(const PrefixParams& p, int dtype, cudaStream_t s);  // prefix_sm100_causal.cu
+int launch_prefix_split(const PrefixParams& p, int dtype, cudaStream_t s);   // prefix_sm100_split.cu
+
+// HYDRAGEN_B200_PREFIX_SOFTMAX = base | split (read once): which softmax organisation the non-causal launches use
+static bool use_split_softmax() {
+  static const bool on = [] {
+    const char* v = getenv("HYDRAGEN_B200_PREFIX_SOFTMAX");
+    return v != nullptr ? (v[0] == 's') : HG_PREFIX_SPLIT_DEFAULT;
+  }();
+  return on;
+}
 
 int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
   if (p.n_groups == 0 || p.q_per_group == 0) return HG_OK;
@@ -893,23 +1077,35 @@ int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
       return set_error(HG_ERR_UNSUPPORTED, "prefix: the causal form takes uniform groups with k_len >= q rows per group and no kv split");
     return launch_prefix_causal(p, dtype, s);
   }
+  if (use_split_softmax()) return launch_prefix_split(p, dtype, s);
   if (dtype == HG_BF16) {
-    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, false>(p, dtype, s);
+    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false, 0>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, false, 0>(p, dtype, s);
   } else {
-    if (p.d == 128) return launch_prefix_inst<__half, 128, false>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__half, 64, false>(p, dtype, s);
+    if (p.d == 128) return launch_prefix_inst<__half, 128, false, 0>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__half, 64, false, 0>(p, dtype, s);
   }
   return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
 }
-#else   // HG_PREFIX_TU_CAUSAL: the second translation unit holds the causal instantiations (compiled in parallel)
+#elif defined(HG_PREFIX_TU_CAUSAL)  // second translation unit: the causal instantiations (compiled in parallel)
 int launch_prefix_causal(const PrefixParams& p, int dtype, cudaStream_t s) {
   if (dtype == HG_BF16) {
-    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, true>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, true>(p, dtype, s);
+    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, true, 0>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, true, 0>(p, dtype, s);
   } else {
-    if (p.d == 128) return launch_prefix_inst<__half, 128, true>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__half, 64, true>(p, dtype, s);
+    if (p.d == 128) return launch_prefix_inst<__half, 128, true, 0>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__half, 64, true, 0>(p, dtype, s);
+  }
+  return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
+}
+#else  // HG_PREFIX_TU_SPLIT: third translation unit: the split-column softmax instantiations
+int launch_prefix_split(const PrefixParams& p, int dtype, cudaStream_t s) {
+  if (dtype == HG_BF16) {
+    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false, 1>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, false, 1>(p, dtype, s);
+  } else {
+    if (p.d == 128) return launch_prefix_inst<__half, 128, false, 1>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__half, 64, false, 1>(p, dtype, s);
   }
   return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
 }

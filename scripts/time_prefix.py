@@ -33,4 +33,4 @@ for _ in range(20):
 e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / (20 * NL)
-print(f"{os.environ.get('HG_EXTRA_NVCC_FLAGS', '-')}: prefix {us:.2f} us/launch, {4.0 * B * H * Lp * D / us / 1e6:.0f} TFLOP/s")
+print(f"{os.environ.get('HG_EXTRA_NVCC_FLAGS', '-')} softmax={os.environ.get('HYDRAGEN_B200_PREFIX_SOFTMAX', 'default')} B={B} L={Lp}: prefix {us:.2f} us/launch, {4.0 * B * H * Lp * D / us / 1e6:.0f} TFLOP/s")
