@@ -59,6 +59,9 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #ifndef HG_PREFIX_SPLIT_DEFAULT
 #define HG_PREFIX_SPLIT_DEFAULT false  // softmax organisation used when HYDRAGEN_B200_PREFIX_SOFTMAX is not set
 #endif
+#ifndef HG_PREFIX_BDELAY_DEFAULT
+#define HG_PREFIX_BDELAY_DEFAULT 700  // cycles tile B's softmax starts after tile A's (0: together); long prefixes only
+#endif
 #ifndef HG_PREFIX_EMU_EVERY
 #define HG_PREFIX_EMU_EVERY 0
 #endif
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(kSplit ? kThreadsSplit : kThreads, 1)
                              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
                              T* __restrict__ out, float* __restrict__ lse, const int32_t* __restrict__ cu_seqlens_k,
                              int q_per_group, int tiles_per_group, int k_len_uniform, int hq, int hkv, float scale_log2,
-                             int kv_splits, int n_q_rows) {
+                             int kv_splits, int n_q_rows, int b_delay) {
   using L = SmemLayout<D>;
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t kIdescQK = make_idesc(kFmt, 0, BLOCK_M, BLOCK_N);
@@ -458,11 +461,12 @@ __global__ void __launch_bounds__(kSplit ? kThreadsSplit : kThreads, 1)
 
   // Register budget (setmaxnreg must sit inside the role branch it applies to): the producer
   // warpgroup gives registers back, the two softmax warpgroups (128 live fp32 scores per thread)
-  // take them: 128 x 88 + 256 x 208 <= 64K.
+  // take them: 128 x 56 + 256 x 224 = 384 x 168, the launch-time allocation (r01h: with 88 / 208 the running max, row
+  // sum and loop state of the softmax threads were spilled to local memory, on the serial path between two blocks).
   // (split-column form: 640 threads x 96 at launch -> 128 x 64 + 512 x 104.)
   if (warp < 4) {
     if constexpr (kSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // =============================== TMA producer ===========================================
     if (elect_one()) {
@@ -729,7 +733,7 @@ __global__ void __launch_bounds__(kSplit ? kThreadsSplit : kThreads, 1)
     }
   } else {
     // =============================== softmax / correction / epilogue ==========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int t = (warp - 4) >> 2;     // tile owned by this warpgroup
     const int rows_valid = min(BLOCK_M, rows_left - t * BLOCK_M);
     if (rows_valid > 0) {
@@ -875,9 +879,19 @@ __global__ void __launch_bounds__(kSplit ? kThreadsSplit : kThreads, 1)
         if (wq == 0 && lane == 0) HG_TRACE(1 + t, j, 5);
       };
 
+      // Phase offset between the two tiles: their softmax warps share one MUFU unit per SM sub-partition, and left
+      // alone they run in lock-step (both in their exp phase, then both outside it).  Starting tile B part of a
+      // block later lets one tile's exponentials run behind the other's TMEM / barrier latencies.
+      // (b_delay: below, after the first scores have arrived.  Measured at cfg#2, r01i: 0 -> 33.0 us, 400 -> 32.9,
+      // 600 -> 32.4, 800 -> 32.2, 1000 -> 32.7, 1300 -> 33.3; no effect at B = 4096.  Short prefixes skip it.)
       {  // prologue: scores and row max of block 0
         if (wq == 0 && lane == 0) HG_TRACE(1 + t, 0, 0);
         mbar_wait(&bars->s_full[t][0], 0);
+        if (t == 1 && b_delay > 0 && n_blocks >= 16) {  // counted from the moment the first scores are there
+          const long long t_start = clock64();
+          while (clock64() - t_start < (long long)b_delay) {
+          }
+        }
         tc_fence_after();
         const uint32_t s_addr = tmem + lane_base + tmem_s(t, 0);
         HG_TMEM_LD32(s_addr + 0, sa, 0);
@@ -992,6 +1006,15 @@ static int make_tmap(CUtensorMap* map, const void* base, int dtype, uint64_t row
   return HG_OK;
 }
 
+// HYDRAGEN_B200_PREFIX_BDELAY (cycles, read once): start offset of tile B's softmax warps
+static int prefix_b_delay() {
+  static const int v = [] {
+    const char* e = getenv("HYDRAGEN_B200_PREFIX_BDELAY");
+    return e != nullptr ? atoi(e) : HG_PREFIX_BDELAY_DEFAULT;
+  }();
+  return v;
+}
+
 template <typename T, int D, bool kCausal, int kSplit>
 static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) {
   using L = SmemLayout<D>;
@@ -1022,7 +1045,7 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, prefix_attn_sm100_kernel<T, D, kCausal, kSplit>, tq, tk, tv, to, (T*)p.out, p.lse, p.cu_seqlens_k, p.q_per_group,
-                                     tiles_per_group, p.k_len, p.hq, p.hkv, p.scale_log2, splits, (int)n_q_rows);
+                                     tiles_per_group, p.k_len, p.hq, p.hkv, p.scale_log2, splits, (int)n_q_rows, prefix_b_delay());
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(HG_ERR_CUDA, "prefix_attn_sm100: launch failed: %s", cudaGetErrorString(e));

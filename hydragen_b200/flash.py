@@ -178,9 +178,10 @@ def flash_attention(q: Tensor, k: Tensor, v: Tensor, causal: bool = False) -> Tu
         return out, lse.permute(0, 2, 1)
     sk = k.shape[1]
     backend = _causal_backend()
-    # prefill chunks go to the tensor cores; tiny ones (a few rows: launch-bound either way) and shapes the tcgen05
-    # kernel does not take (fp32, other head dims, sk < sq) stay on the CUDA-core kernel
-    use_tc = q.dtype in _TC_DTYPES and d in _TC_HEAD_DIMS and sk >= sq and backend != "rowwise" and (backend == "tcgen05" or sq >= 16)
+    # prefill chunks of at least one key block go to the tensor cores; shorter ones (launch-bound either way; the
+    # CUDA-core kernel keeps P in fp32) and shapes the tcgen05 kernel does not take (fp32, other head dims, sk < sq)
+    # stay on the CUDA-core kernel
+    use_tc = q.dtype in _TC_DTYPES and d in _TC_HEAD_DIMS and sk >= sq and backend != "rowwise" and (backend == "tcgen05" or sq >= 64)
     if backend == "tcgen05" and not use_tc:
         raise ValueError(f"tcgen05 causal kernel does not take dtype {q.dtype} / head_dim {d} / sq {sq} > sk {sk}")
     if use_tc:
