@@ -332,13 +332,15 @@ def run_ours(a):
     # events on the launching stream.  (Events around eager launches would time the Python launch gaps.)
     pre_out = [None] * L
 
-    def only_prefix():
+    from hydragen_b200.flash import prefix_attention_partials
+
+    def only_prefix():  # the same launch the step makes: split-KV when the local heads alone do not fill the SMs (TP ranks)
         for i in range(L):
-            pre_out[i] = prefix_attention_grouped(qs[i], shared_k[i], shared_v[i], n_groups=1)
+            pre_out[i] = prefix_attention_partials(qs[i], shared_k[i], shared_v[i], n_groups=1, max_splits=_lib.HG_MAX_COMBINE)
 
     def only_suffix():
         for i in range(L):
-            decode_attention_fused(qs[i], kn[i], vn[i], pos, uniq[i, 0], uniq[i, 1], [pre_out[i][0]], [pre_out[i][1]])
+            decode_attention_fused(qs[i], kn[i], vn[i], pos, uniq[i, 0], uniq[i, 1], pre_out[i][0], pre_out[i][1])
 
     def time_kernel_graph(fn, reps=20):
         fn()
@@ -380,7 +382,9 @@ def run_ours(a):
     pre_flops = 4.0 * B * H * a.prefix_len * D
     esz = 2
     # new K,V rows read + appended, older K,V rows read, q + prefix partial + out, 2 LSE rows
-    suf_bytes = 4.0 * B * HKV * D * esz + 2.0 * B * (a.suffix_len - 1) * HKV * D * esz + 3.0 * B * H * D * esz + 2.0 * B * H * 4
+    n_part = len(pre_out[0][0])  # prefix partials merged by the decode launch (1 unless split-KV)
+    suf_bytes = (4.0 * B * HKV * D * esz + 2.0 * B * (a.suffix_len - 1) * HKV * D * esz + (2.0 + n_part) * B * H * D * esz
+                 + (1.0 + n_part) * B * H * 4)
     roofline = {"kernel": "prefix_attn_sm100_kernel (tcgen05)", "bound": "tensor", "achieved": pre_flops / pre_t / 1e6, "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": pre_flops / pre_t / 1e6 / tf_peak, "traffic": None, "us_per_launch": pre_t,
                 "algorithmic_flop_per_launch": pre_flops, "peak_source": peak_src}
@@ -449,6 +453,7 @@ def run_ours(a):
                         "sample": f"1 of {L} layers of the same workload, fp32 torch, median of {n} runs (~{a.cpu_seconds:.0f} s); tokens/s extrapolated x{L}",
                         "ms_per_layer": t_layer * 1e3}
 
+    used_graph = graph is not None
     full_model = None
     if a.full_model and world == 1:
         del graph, step
@@ -466,7 +471,7 @@ def run_ours(a):
             "config": {"workload": workload_name(a), "scope": "attention hot path of one decode step (prefix + fused kv-append/suffix/combine per layer); projections/MLP/sampling out of scope",
                        "parallelism": (f"tp{world} (head axis, 1 all-reduce of [B,{hidden}] bf16 per layer: " + ("hg_allreduce_multimem NVLS kernel" if nvls is not None else "NCCL") + ")") if world > 1 else "single GPU",
                        "l2": f"inputs larger than L2: {L} layers x distinct caches cycle {L * (2 * a.prefix_len * HKV * D * 2 + 4 * B * H * D * 2) / 2**20:.0f}+ MiB per step through a 126 MB L2",
-                       "cuda_graph": graph is not None},
+                       "cuda_graph": used_graph},
             "roofline": roofline, "roofline_suffix": roofline_suffix, "roofline_rope": roofline_rope, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
         }

@@ -19,13 +19,25 @@ namespace hg {
 
 namespace {
 
+// Round a pair of fp32 values to T and back (the rounding torch applies after every elementwise operation).
+// bf16: ONE packed conversion (F2FP on the ALU/FMA side) + two bit operations -- the scalar cvt.rn.bf16.f32 is an XU
+// (MUFU-pipe) instruction and made the first version of this kernel conversion-bound (r01k: XU 53 % busy, 9.0 us).
 template <typename T>
-__device__ __forceinline__ float rnd(float x) {
-  return to_f32<T>(from_f32<T>(x));
+__device__ __forceinline__ void rnd2(float& a, float& b);
+template <>
+__device__ __forceinline__ void rnd2<float>(float&, float&) {}
+template <>
+__device__ __forceinline__ void rnd2<__nv_bfloat16>(float& a, float& b) {
+  uint32_t u;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a));  // first source -> upper half
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xffff0000u);
 }
 template <>
-__device__ __forceinline__ float rnd<float>(float x) {
-  return x;
+__device__ __forceinline__ void rnd2<__half>(float& a, float& b) {
+  const float2 r = __half22float2(__floats2half2_rn(a, b));
+  a = r.x;
+  b = r.y;
 }
 
 template <typename T, bool I64>
@@ -69,8 +81,12 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       // first half:  x_lo * cos + (-x_hi) * sin;   second half:  x_hi * cos + x_lo * sin
-      ol[i] = __fadd_rn(rnd<T>(__fmul_rn(xl[i], cl[i])), rnd<T>(__fmul_rn(-xh[i], sl[i])));
-      oh[i] = __fadd_rn(rnd<T>(__fmul_rn(xh[i], ch[i])), rnd<T>(__fmul_rn(xl[i], sh[i])));
+      float a0 = __fmul_rn(xl[i], cl[i]), a1 = __fmul_rn(-xh[i], sl[i]);
+      float b0 = __fmul_rn(xh[i], ch[i]), b1 = __fmul_rn(xl[i], sh[i]);
+      rnd2<T>(a0, a1);
+      rnd2<T>(b0, b1);
+      ol[i] = __fadd_rn(a0, a1);
+      oh[i] = __fadd_rn(b0, b1);
     }
     st_v4(dst + e, Vec16<T>::pack(ol));
     st_v4(dst + half + e, Vec16<T>::pack(oh));
