@@ -97,3 +97,44 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_new_entry_points_validate_without_gpu(built_lib):
+    """hg_rope_qk / hg_causal_attn_fwd reject bad arguments before any CUDA call."""
+    from hydragen_b200 import _lib
+
+    lib = _lib.load()
+    # rope: head_dim must be a multiple of 16 for 16-bit dtypes
+    rc = lib.hg_rope_qk(None, None, None, None, None, None, None, 1, 4, 2, 2, 24, 48, 48, 48, 48, 16, 1, None)
+    assert rc == -2 and b"head_dim" in lib.hg_last_error()
+    # rope: null tensors with rows > 0
+    rc = lib.hg_rope_qk(None, None, None, None, None, None, None, 1, 4, 2, 2, 64, 128, 128, 128, 128, 16, 1, None)
+    assert rc == -1 and b"null" in lib.hg_last_error()
+    # rope: a row stride smaller than heads * head_dim
+    buf = ctypes.c_void_p(4096)
+    rc = lib.hg_rope_qk(buf, buf, buf, buf, buf, buf, buf, 1, 4, 2, 2, 64, 64, 128, 128, 128, 16, 1, None)
+    assert rc == -1 and b"row stride" in lib.hg_last_error()
+    # rope: zero rows is a no-op (no device needed)
+    assert lib.hg_rope_qk(None, None, None, None, None, None, None, 0, 0, 2, 2, 64, 128, 128, 128, 128, 16, 1, None) == 0
+    # causal: needs hg_init; after that sk < sq is unsupported -- without a GPU only the first is reachable
+    rc = lib.hg_causal_attn_fwd(None, None, None, None, None, 1, 8, 4, 2, 2, 128, 256, 256, 0.1, 1, None)
+    assert rc == -4
+
+
+def test_rope_and_causal_refuse_cpu_tensors():
+    from hydragen_b200._lib import HydragenB200Error
+    from hydragen_b200.flash import flash_attention
+    from hydragen_b200.rope import apply_rotary_pos_emb
+
+    q = torch.randn(2, 64, 4, 64, dtype=torch.bfloat16)
+    cos = torch.zeros(128, 64, dtype=torch.bfloat16)
+    pos = torch.zeros(2, 64, dtype=torch.long)
+    with pytest.raises(HydragenB200Error):
+        apply_rotary_pos_emb(q, q.clone(), cos, cos, pos)
+    with pytest.raises(HydragenB200Error):
+        flash_attention(q, q, q, causal=True)
+    # argument errors are raised before the device is touched
+    with pytest.raises(ValueError):
+        apply_rotary_pos_emb(q, q.clone(), cos.float(), cos.float(), pos)
+    with pytest.raises(NotImplementedError):
+        apply_rotary_pos_emb(q, q.clone(), cos, cos, pos, unsqueeze_dim=1)
