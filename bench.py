@@ -401,6 +401,7 @@ def run_ours(a):
             tr = json.load(open(prof))
             roofline["traffic"] = tr.get("prefix_dram_bytes_per_launch")
             roofline_suffix["traffic"] = tr.get("suffix_dram_bytes_per_launch")
+            roofline_rope["traffic"] = tr.get("rope_dram_bytes_per_launch")
         except Exception:
             pass
 

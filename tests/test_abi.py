@@ -138,3 +138,22 @@ def test_rope_and_causal_refuse_cpu_tensors():
         apply_rotary_pos_emb(q, q.clone(), cos.float(), cos.float(), pos)
     with pytest.raises(NotImplementedError):
         apply_rotary_pos_emb(q, q.clone(), cos, cos, pos, unsqueeze_dim=1)
+
+
+def test_row_view_helpers_accept_fused_projection_views():
+    """Host logic of the shims: which strided [b, s, h, d] views can be handed to the kernels without a copy."""
+    from hydragen_b200.flash import _rows_view
+    from hydragen_b200.rope import _row_stride
+
+    qkv = torch.zeros(6, 1, 3 * 4 * 64)
+    q = qkv[..., : 4 * 64].unflatten(-1, (4, 64))          # decode: q rows inside a fused qkv buffer
+    assert _rows_view(q) == 3 * 4 * 64 and _row_stride(q) == 3 * 4 * 64
+    x = torch.zeros(2, 5, 4, 64)
+    assert _rows_view(x) == 256 and _row_stride(x) == 256   # dense
+    assert _rows_view(x[:, :3]) is None and _row_stride(x[:, :3]) is None      # (b, s) axes do not collapse
+    assert _rows_view(x[:1, :3]) == 256 and _row_stride(x[:1, :3]) == 256      # single batch entry: fine
+    assert _rows_view(x[:, :, ::2]) is None and _row_stride(x[:, :, ::2]) is None  # heads not dense
+    assert _rows_view(x.transpose(1, 2)) is None
+    cache = torch.zeros(3, 16, 2, 64)
+    assert _rows_view(cache[:, :9]) is None                 # a cache prefix slice needs a copy ...
+    assert _rows_view(cache[:1, :9]) == 128                 # ... unless it is one sequence
