@@ -29,10 +29,20 @@
 //                    packed fp32x2; P_t stored to TMEM as packed 16-bit; lazy rescale of O_t (only
 //                    when the running max grows by more than 2^8); epilogue O_t / l -> swizzled
 //                    smem (the dead Q_t tile) -> TMA store; LSE written directly in [b, nq, hq].
+//                    setmaxnreg: 56 registers for warps 0-3, 224 for the softmax warps (no spills in the loop)
 //
 // All producer/consumer edges are mbarriers (TMA complete_tx, tcgen05.commit, thread arrives); there
 // is no __syncthreads in the main loop.  Split-KV (kv_splits > 1): the CTAs of one tile each take a
 // contiguous range of key blocks and write their own partial (out, lse).
+//
+// Instantiations (one translation unit each, compiled in parallel: this file is also #included by
+// prefix_sm100_causal.cu and prefix_sm100_split.cu):
+//   <T, D, kCausal = false, kSplit = 0>  the decode hot path (hg_prefix_attn_fwd / _split_fwd)
+//   <T, D, kCausal = true,  kSplit = 0>  prefill: bottom-right aligned causal mask inside every group
+//                                        (hg_causal_attn_fwd): row tiles heavy-first, only the visible key
+//                                        blocks are streamed, masks only in the blocks crossing the diagonal
+//   <T, D, kCausal = false, kSplit = 1>  experimental split-column softmax (two warpgroups per tile); measured
+//                                        slower, selected only by HYDRAGEN_B200_PREFIX_SOFTMAX=split
 //
 // Algorithmic work per CTA: 4 * rows * k_len * d FLOP.  Bound: tensor pipe (AI ~ 680 FLOP/B at the
 // 7B config), with the MUFU exp2 rate (16/clk/SM == the 128x128x128 MMA rate) the co-limiter.
