@@ -43,6 +43,8 @@
 //                                        blocks are streamed, masks only in the blocks crossing the diagonal
 //   <T, D, kCausal = false, kSplit = 1>  experimental split-column softmax (two warpgroups per tile); measured
 //                                        slower, selected only by HYDRAGEN_B200_PREFIX_SOFTMAX=split
+//   <T, D, kCausal = false, kSplit = 2>  experimental non-pipelined softmax loop (prefix_sm100_simple.cu),
+//                                        HYDRAGEN_B200_PREFIX_SOFTMAX=simple
 //
 // Algorithmic work per CTA: 4 * rows * k_len * d FLOP.  Bound: tensor pipe (AI ~ 680 FLOP/B at the
 // 7B config), with the MUFU exp2 rate (16/clk/SM == the 128x128x128 MMA rate) the co-limiter.
@@ -66,8 +68,8 @@ constexpr uint32_t kTmemCols = 512;
 __host__ __device__ constexpr uint32_t tmem_s(int t, int b) { return (uint32_t)t * 128u + (uint32_t)b * 64u; }  // S_t buffer b (P aliases its first 32 columns)
 __host__ __device__ constexpr uint32_t tmem_o(int t) { return 256u + (uint32_t)t * 128u; }                       // O_t
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-#ifndef HG_PREFIX_SPLIT_DEFAULT
-#define HG_PREFIX_SPLIT_DEFAULT false  // softmax organisation used when HYDRAGEN_B200_PREFIX_SOFTMAX is not set
+#ifndef HG_PREFIX_SOFTMAX_DEFAULT
+#define HG_PREFIX_SOFTMAX_DEFAULT 0  // softmax organisation used when HYDRAGEN_B200_PREFIX_SOFTMAX is not set (0 base)
 #endif
 #ifndef HG_PREFIX_BDELAY_DEFAULT
 #define HG_PREFIX_BDELAY_DEFAULT 700  // cycles tile B's softmax starts after tile A's (0: together); long prefixes only
@@ -339,7 +341,7 @@ struct Barriers {
 
 }  // namespace
 
-#if defined(HG_PREFIX_TRACE) && !defined(HG_PREFIX_TU_CAUSAL) && !defined(HG_PREFIX_TU_SPLIT)
+#if defined(HG_PREFIX_TRACE) && !defined(HG_PREFIX_TU_CAUSAL) && !defined(HG_PREFIX_TU_SPLIT) && !defined(HG_PREFIX_TU_SIMPLE)
 // Development aid (never compiled into the shipped library): clock64 stamps of CTA (0,0).
 // Layout: [role][block j][slot]; role 0 = MMA thread, 1 = softmax warp of tile A, 2 = tile B.
 __device__ long long g_trace[3 * 64 * 8];
@@ -361,7 +363,7 @@ __device__ long long g_trace[3 * 64 * 8];
 // instead of two hide each other's TMEM / MUFU / barrier latencies (r01e: the two-warp form keeps the MUFU unit
 // only ~55 % busy); the two half-row maxima meet through shared memory and a 64-thread named barrier per block.
 template <typename T, int D, bool kCausal, int kSplit>
-__global__ void __launch_bounds__(kSplit ? kThreadsSplit : kThreads, 1)
+__global__ void __launch_bounds__(kSplit == 1 ? kThreadsSplit : kThreads, 1)
     prefix_attn_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
                              T* __restrict__ out, float* __restrict__ lse, const int32_t* __restrict__ cu_seqlens_k,
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(kSplit ? kThreadsSplit : kThreads, 1)
       mbar_init(&bars->o_full[i], 1);
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bars->s_full[i][b], 1);
-        mbar_init(&bars->p_full[i][b], BLOCK_M * (kSplit ? 2 : 1));
+        mbar_init(&bars->p_full[i][b], BLOCK_M * (kSplit == 1 ? 2 : 1));
       }
     }
     for (int i = 0; i < kStages; ++i) {
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(kSplit ? kThreadsSplit : kThreads, 1)
   // sum and loop state of the softmax threads were spilled to local memory, on the serial path between two blocks).
   // (split-column form: 640 threads x 96 at launch -> 128 x 64 + 512 x 104.)
   if (warp < 4) {
-    if constexpr (kSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if constexpr (kSplit == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // =============================== TMA producer ===========================================
@@ -583,7 +585,7 @@ __global__ void __launch_bounds__(kSplit ? kThreadsSplit : kThreads, 1)
       }
     }
   }
-  } else if constexpr (kSplit) {
+  } else if constexpr (kSplit == 1) {
     // =============================== softmax, split-column form ===============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int sw = warp - 4;          // 0 .. 15
@@ -761,14 +763,90 @@ __global__ void __launch_bounds__(kSplit ? kThreadsSplit : kThreads, 1)
       // requests in groups of 8, so that the in-order warp always has independent work behind them and
       // the two softmax warps sharing an SM sub-partition do not convoy on the MUFU unit.  Two score
       // register arrays alternate between "being exponentiated" and "being fetched".
-      uint32_t sa[BLOCK_N], sb[BLOCK_N];
-      float m_blk;
       // first key (group-relative) this thread's row may NOT see; tile_lim: the same for the tile's first row
       const int row_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + row + causal_off + 1 : 0x7fffffff;
       const int tile_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + causal_off + 1 : 0x7fffffff;
       const bool ragged = (k_len % BLOCK_N) != 0;
       // block jb holds a key some row of this tile must not see (warp-uniform)
       auto needs_mask = [&](int jb) { return (ragged && jb + 1 == n_blocks) || (jb + 1) * BLOCK_N > tile_end; };
+      if constexpr (kSplit == 2) {
+        // "simple" form (experimental, HYDRAGEN_B200_PREFIX_SOFTMAX=simple): no software pipelining -- per block:
+        // wait for S_t(j), fetch it, row max, (lazy rescale), exp / sum / pack, store P_t(j), arrive.  The isolated
+        // instruction stream in this shape needs 1279 cycles per block pair with two warps per sub-partition
+        // (scripts/microbench/softmax_stream.cu, r01r) against the 1625 of the pipelined loop inside the kernel.
+        for (int j = 0; j < n_blocks; ++j) {
+          const int b = j & 1;
+          const uint32_t s_addr = tmem + lane_base + tmem_s(t, b);
+          mbar_wait(&bars->s_full[t][b], (j >> 1) & 1);
+          tc_fence_after();
+          uint32_t sc[BLOCK_N];
+          HG_TMEM_LD32(s_addr + 0, sc, 0);
+          HG_TMEM_LD32(s_addr + 32, sc, 32);
+          tmem_wait_ld();
+          if (needs_mask(j)) {
+            const int rem = min(k_len, row_end) - j * BLOCK_N;
+#pragma unroll
+            for (int c = 0; c < BLOCK_N; ++c)
+              if (c >= rem) sc[c] = 0xff800000u;  // -inf
+          }
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < BLOCK_N; c += 8) {
+            mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(sc[c + 0]), __uint_as_float(sc[c + 1])));
+            mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(sc[c + 2]), __uint_as_float(sc[c + 3])));
+            mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(sc[c + 4]), __uint_as_float(sc[c + 5])));
+            mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(sc[c + 6]), __uint_as_float(sc[c + 7])));
+          }
+          const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+          if (j == 0) {
+            m_used = m_new;
+          } else {
+            const bool need = (m_new - m_used) * scale_log2 > kRescaleThreshold;
+            if (__any_sync(0xffffffffu, need)) {
+              mbar_wait(&bars->pv_done[t], (j - 1) & 1);
+              tc_fence_after();
+              const float alpha = need ? fast_exp2((m_used - m_new) * scale_log2) : 1.f;
+              if (need) {
+                m_used = m_new;
+                l *= alpha;
+              }
+#pragma unroll
+              for (int c0 = 0; c0 < D; c0 += 32) {
+                uint32_t o[32];
+                HG_TMEM_LD32(o_addr + c0, o, 0);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+                HG_TMEM_ST32(o_addr + c0, o, 0);
+              }
+            }
+          }
+          const float neg_mc = -m_used * scale_log2;
+          const uint64_t scale2 = pack_f2(scale_log2, scale_log2), neg2 = pack_f2(neg_mc, neg_mc);
+          uint64_t ps2[2] = {0ull, 0ull};
+          uint32_t pk[BLOCK_N / 2];
+#pragma unroll
+          for (int c = 0; c < BLOCK_N; c += 2) {
+            float x0, x1;
+            unpack_f2(ffma2(pack_f2(__uint_as_float(sc[c]), __uint_as_float(sc[c + 1])), scale2, neg2), x0, x1);
+            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+            ps2[(c >> 1) & 1] = fadd2(ps2[(c >> 1) & 1], pack_f2(p0, p1));
+            pk[c >> 1] = pack2<T>(p0, p1);
+          }
+          HG_TMEM_ST16(s_addr, pk, 0);
+          HG_TMEM_ST16(s_addr + 16, pk, 16);
+          {
+            float a0, a1;
+            unpack_f2(fadd2(ps2[0], ps2[1]), a0, a1);
+            l += a0 + a1;
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bars->p_full[t][b]);
+        }
+      } else {
+      uint32_t sa[BLOCK_N], sb[BLOCK_N];
+      float m_blk;
       auto mask_tail = [&](uint32_t(&x)[BLOCK_N], int j) {
         const int rem = min(k_len, row_end) - j * BLOCK_N;
 #pragma unroll
@@ -925,6 +1003,7 @@ __global__ void __launch_bounds__(kSplit ? kThreadsSplit : kThreads, 1)
           else body(j, sb, sa, std::true_type{}, std::false_type{});
         }
       }
+      }  // pipelined form
 
       // ---- epilogue --------------------------------------------------------------------------
       mbar_wait(&bars->o_full[t], 0);
@@ -1046,7 +1125,7 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   const int tiles_per_group = (p.q_per_group + kTiles * BLOCK_M - 1) / (kTiles * BLOCK_M);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(p.n_groups * tiles_per_group * splits), (unsigned)p.hq, 1);
-  cfg.blockDim = dim3(kSplit ? kThreadsSplit : kThreads);
+  cfg.blockDim = dim3(kSplit == 1 ? kThreadsSplit : kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -1063,7 +1142,7 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   return check_launch("prefix_attn_sm100");
 }
 
-#if !defined(HG_PREFIX_TU_CAUSAL) && !defined(HG_PREFIX_TU_SPLIT)
+#if !defined(HG_PREFIX_TU_CAUSAL) && !defined(HG_PREFIX_TU_SPLIT) && !defined(HG_PREFIX_TU_SIMPLE)
 #ifdef HG_PREFIX_TRACE
 extern "C" int hg_debug_read_trace(long long* host_buf, int n) {
   cudaDeviceSynchronize();
@@ -1086,14 +1165,19 @@ int suggest_prefix_splits(int n_groups, int q_per_group, int hq, int max_k_len, 
 
 int launch_prefix_causal(const PrefixParams& p, int dtype, cudaStream_t s);  // prefix_sm100_causal.cu
 int launch_prefix_split(const PrefixParams& p, int dtype, cudaStream_t s);   // prefix_sm100_split.cu
+int launch_prefix_simple(const PrefixParams& p, int dtype, cudaStream_t s);  // prefix_sm100_simple.cu
 
-// HYDRAGEN_B200_PREFIX_SOFTMAX = base | split (read once): which softmax organisation the non-causal launches use
-static bool use_split_softmax() {
-  static const bool on = [] {
-    const char* v = getenv("HYDRAGEN_B200_PREFIX_SOFTMAX");
-    return v != nullptr ? (v[0] == 's') : HG_PREFIX_SPLIT_DEFAULT;
+// HYDRAGEN_B200_PREFIX_SOFTMAX = base | split | simple (read once): which softmax organisation the non-causal
+// launches use (0 base: software pipelined, the default; 1 split-column; 2 simple: not pipelined)
+static int softmax_variant() {
+  static const int v = [] {
+    const char* e = getenv("HYDRAGEN_B200_PREFIX_SOFTMAX");
+    if (e == nullptr) return HG_PREFIX_SOFTMAX_DEFAULT;
+    if (e[0] == 's' && e[1] == 'p') return 1;
+    if (e[0] == 's' && e[1] == 'i') return 2;
+    return 0;
   }();
-  return on;
+  return v;
 }
 
 int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
@@ -1110,7 +1194,8 @@ int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
       return set_error(HG_ERR_UNSUPPORTED, "prefix: the causal form takes uniform groups with k_len >= q rows per group and no kv split");
     return launch_prefix_causal(p, dtype, s);
   }
-  if (use_split_softmax()) return launch_prefix_split(p, dtype, s);
+  if (softmax_variant() == 1) return launch_prefix_split(p, dtype, s);
+  if (softmax_variant() == 2) return launch_prefix_simple(p, dtype, s);
   if (dtype == HG_BF16) {
     if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false, 0>(p, dtype, s);
     if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, false, 0>(p, dtype, s);
@@ -1128,6 +1213,17 @@ int launch_prefix_causal(const PrefixParams& p, int dtype, cudaStream_t s) {
   } else {
     if (p.d == 128) return launch_prefix_inst<__half, 128, true, 0>(p, dtype, s);
     if (p.d == 64) return launch_prefix_inst<__half, 64, true, 0>(p, dtype, s);
+  }
+  return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
+}
+#elif defined(HG_PREFIX_TU_SIMPLE)  // fourth translation unit: the non-pipelined softmax instantiations
+int launch_prefix_simple(const PrefixParams& p, int dtype, cudaStream_t s) {
+  if (dtype == HG_BF16) {
+    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false, 2>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, false, 2>(p, dtype, s);
+  } else {
+    if (p.d == 128) return launch_prefix_inst<__half, 128, false, 2>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__half, 64, false, 2>(p, dtype, s);
   }
   return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
 }
