@@ -45,6 +45,9 @@
 //                                        slower, selected only by HYDRAGEN_B200_PREFIX_SOFTMAX=split
 //   <T, D, kCausal = false, kSplit = 2>  experimental non-pipelined softmax loop (prefix_sm100_simple.cu),
 //                                        HYDRAGEN_B200_PREFIX_SOFTMAX=simple
+//   <T, D, kCausal = false, kSplit = 3>  alternate-block softmax: four softmax warps per sub-partition without a
+//                                        per-block exchange (prefix_sm100_alt.cu, HYDRAGEN_B200_PREFIX_SOFTMAX=alt);
+//                                        written after the GPU budget of round 1 was spent: NOT yet run on hardware
 //
 // Algorithmic work per CTA: 4 * rows * k_len * d FLOP.  Bound: tensor pipe (AI ~ 680 FLOP/B at the
 // 7B config), with the MUFU exp2 rate (16/clk/SM == the 128x128x128 MMA rate) the co-limiter.
@@ -337,11 +340,13 @@ struct Barriers {
   uint64_t pv_done[kTiles];                       // one phase per PV_t(j) (lazy-rescale path only)
   uint64_t o_full[kTiles];                        // O_t complete
   uint32_t tmem_base;
+  uint32_t pad_;
+  uint64_t m_ready[kTiles][4][2];  // alternate-block softmax only: reference max of a block published (per lane quarter, block parity)
 };
 
 }  // namespace
 
-#if defined(HG_PREFIX_TRACE) && !defined(HG_PREFIX_TU_CAUSAL) && !defined(HG_PREFIX_TU_SPLIT) && !defined(HG_PREFIX_TU_SIMPLE)
+#if defined(HG_PREFIX_TRACE) && !defined(HG_PREFIX_TU_CAUSAL) && !defined(HG_PREFIX_TU_SPLIT) && !defined(HG_PREFIX_TU_SIMPLE) && !defined(HG_PREFIX_TU_ALT)
 // Development aid (never compiled into the shipped library): clock64 stamps of CTA (0,0).
 // Layout: [role][block j][slot]; role 0 = MMA thread, 1 = softmax warp of tile A, 2 = tile B.
 __device__ long long g_trace[3 * 64 * 8];
@@ -363,7 +368,7 @@ __device__ long long g_trace[3 * 64 * 8];
 // instead of two hide each other's TMEM / MUFU / barrier latencies (r01e: the two-warp form keeps the MUFU unit
 // only ~55 % busy); the two half-row maxima meet through shared memory and a 64-thread named barrier per block.
 template <typename T, int D, bool kCausal, int kSplit>
-__global__ void __launch_bounds__(kSplit == 1 ? kThreadsSplit : kThreads, 1)
+__global__ void __launch_bounds__((kSplit == 1 || kSplit == 3) ? kThreadsSplit : kThreads, 1)
     prefix_attn_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
                              T* __restrict__ out, float* __restrict__ lse, const int32_t* __restrict__ cu_seqlens_k,
@@ -440,6 +445,10 @@ __global__ void __launch_bounds__(kSplit == 1 ? kThreadsSplit : kThreads, 1)
       mbar_init(&bars->q_full[i], 1);
       mbar_init(&bars->pv_done[i], 1);
       mbar_init(&bars->o_full[i], 1);
+      if constexpr (kSplit == 3) {
+        for (int q = 0; q < 4; ++q)
+          for (int b = 0; b < 2; ++b) mbar_init(&bars->m_ready[i][q][b], 32);
+      }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bars->s_full[i][b], 1);
         mbar_init(&bars->p_full[i][b], BLOCK_M * (kSplit == 1 ? 2 : 1));
@@ -477,7 +486,7 @@ __global__ void __launch_bounds__(kSplit == 1 ? kThreadsSplit : kThreads, 1)
   // sum and loop state of the softmax threads were spilled to local memory, on the serial path between two blocks).
   // (split-column form: 640 threads x 96 at launch -> 128 x 64 + 512 x 104.)
   if (warp < 4) {
-    if constexpr (kSplit == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if constexpr (kSplit == 1 || kSplit == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // =============================== TMA producer ===========================================
@@ -741,6 +750,204 @@ __global__ void __launch_bounds__(kSplit == 1 ? kThreadsSplit : kThreads, 1)
       }
       if (half == 0 && row < rows_valid && lse != nullptr)
         lse[(int64_t)(tile_row0 + row) * hq + head] = (l > 0.f) ? (m_used * scale_log2 + fast_log2(l)) * kLn2 : -INFINITY;
+      tc_fence_before();
+    }
+  } else if constexpr (kSplit == 3) {
+    // =============================== softmax, alternate-block form ============================
+    // Two warpgroups per tile; the warps that own the same 32 rows take the key blocks in turn (even / odd), each with
+    // its own S/P buffer (the double buffer IS the block parity), so four softmax warps share a sub-partition without
+    // a per-block exchange of scores.  What the two share per row is the lazily updated reference max: the warp of
+    // block j publishes the reference it used (shared memory + an mbarrier with 32 arrivals) as soon as it has the
+    // row max of its block -- long before it is done with the block -- and the warp of block j+1 picks it up.  Each
+    // warp keeps its own partial row sum relative to the reference it last saw; they meet once, in the epilogue.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int sw = warp - 4;          // 0 .. 15
+    const int t = sw >> 3;            // tile owned by this pair of warpgroups
+    const int par = (sw >> 2) & 1;    // this warp takes key blocks j with j % 2 == par (and, in the epilogue, D/2 columns of O)
+    const int rows_valid = min(BLOCK_M, rows_left - t * BLOCK_M);
+    if (rows_valid > 0) {
+      constexpr int DH = D / 2;
+      const int half = par;
+      const int wq = warp & 3;        // == sw % 4: the TMEM lane quarter this warp may access
+      const int row = wq * 32 + lane;
+      const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+      const uint32_t o_all = tmem + lane_base + tmem_o(t);        // every column of this row of O_t (lazy rescale)
+      const uint32_t o_addr = o_all + (uint32_t)(half * DH);      // the columns this warp writes out
+      const uint32_t s_addr = tmem + lane_base + tmem_s(t, par);  // this warp's S / P buffer
+      float* xchg = reinterpret_cast<float*>(smem + L::kXchg);
+      volatile float* m_mine = xchg + ((par * kTiles + t) * 2 + 0) * BLOCK_M + row;          // reference published by this warp
+      volatile float* m_other = xchg + (((par ^ 1) * kTiles + t) * 2 + 0) * BLOCK_M + row;   // ... by its partner
+      volatile float* l_mine = xchg + ((par * kTiles + t) * 2 + 1) * BLOCK_M + row;
+      volatile float* l_other = xchg + (((par ^ 1) * kTiles + t) * 2 + 1) * BLOCK_M + row;
+      uint64_t* ready_mine = &bars->m_ready[t][wq][par];
+      uint64_t* ready_other = &bars->m_ready[t][wq][par ^ 1];
+      const int pair_bar = 1 + t * 4 + wq;  // the two warps that own the same 32 rows (named barriers 1..8)
+      float m_w = -INFINITY;  // reference this warp's partial row sum is expressed in
+      float l = 0.f;
+      const int row_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + row + causal_off + 1 : 0x7fffffff;
+      const int tile_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + causal_off + 1 : 0x7fffffff;
+      const bool ragged = (k_len % BLOCK_N) != 0;
+      for (int j = par; j < n_blocks; j += 2) {
+        mbar_wait(&bars->s_full[t][par], (j >> 1) & 1);
+        tc_fence_after();
+        const bool masked = (ragged && j + 1 == n_blocks) || (j + 1) * BLOCK_N > tile_end;  // warp-uniform
+        const int rem = min(k_len, row_end) - j * BLOCK_N;
+        uint32_t sc[32];
+        // ---- pass 1: row max of the block (the scores are fetched again in pass 2: TMEM reads are cheap, registers are not)
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          HG_TMEM_LD32(s_addr + h * 32, sc, 0);
+          tmem_wait_ld();
+          if (masked) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (h * 32 + c >= rem) sc[c] = 0xff800000u;  // -inf
+          }
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(sc[c + 0]), __uint_as_float(sc[c + 1])));
+            mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(sc[c + 2]), __uint_as_float(sc[c + 3])));
+            mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(sc[c + 4]), __uint_as_float(sc[c + 5])));
+            mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(sc[c + 6]), __uint_as_float(sc[c + 7])));
+          }
+        }
+        const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        // ---- the reference this block is exponentiated against
+        float m_used;
+        if (j == 0) {
+          m_used = m_blk;
+        } else {
+          mbar_wait(ready_other, ((j - 1) >> 1) & 1);  // block j-1's warp has published its reference
+          const float m_prev = *m_other;
+          const float m_new = fmaxf(m_prev, m_blk);
+          const bool need = (m_new - m_prev) * scale_log2 > kRescaleThreshold;
+          m_used = m_prev;
+          if (__any_sync(0xffffffffu, need)) {
+            // rare: O_t must be complete up to P_t(j-1) V_{j-1} before it is rescaled in place; P_t(j) has not been
+            // released yet, and block j+1's warp cannot release P_t(j+1)'s rescale before P_t(j) V_j is done.
+            mbar_wait(&bars->pv_done[t], (j - 1) & 1);
+            tc_fence_after();
+            const float alpha = need ? fast_exp2((m_prev - m_new) * scale_log2) : 1.f;
+            if (need) m_used = m_new;
+#pragma unroll
+            for (int c0 = 0; c0 < D; c0 += 32) {
+              uint32_t o[32];
+              HG_TMEM_LD32(o_all + c0, o, 0);
+              tmem_wait_ld();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+              HG_TMEM_ST32(o_all + c0, o, 0);
+            }
+          }
+        }
+        *m_mine = m_used;
+        mbar_arrive(ready_mine);  // release: the store above is visible to whoever sees this phase complete
+        if (m_w != m_used) {      // bring this warp's partial row sum to the reference in force (first block: 0 * 0)
+          l *= fast_exp2((m_w - m_used) * scale_log2);
+          m_w = m_used;
+        }
+        // ---- pass 2: exponentials, row sum, P_t(j)
+        const float neg_mc = -m_used * scale_log2;
+        const uint64_t scale2 = pack_f2(scale_log2, scale_log2), neg2 = pack_f2(neg_mc, neg_mc);
+        uint64_t ps2[2] = {0ull, 0ull};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          HG_TMEM_LD32(s_addr + h * 32, sc, 0);
+          tmem_wait_ld();
+          if (masked) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (h * 32 + c >= rem) sc[c] = 0xff800000u;
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float x0, x1;
+            unpack_f2(ffma2(pack_f2(__uint_as_float(sc[c]), __uint_as_float(sc[c + 1])), scale2, neg2), x0, x1);
+            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+            ps2[(c >> 1) & 1] = fadd2(ps2[(c >> 1) & 1], pack_f2(p0, p1));
+            pk[c >> 1] = pack2<T>(p0, p1);
+          }
+          // keys [h*32, h*32+32) -> columns [h*16, h*16+16): only columns whose scores this thread has already consumed
+          HG_TMEM_ST16(s_addr + h * 16, pk, 0);
+        }
+        {
+          float a0, a1;
+          unpack_f2(fadd2(ps2[0], ps2[1]), a0, a1);
+          l += a0 + a1;
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bars->p_full[t][par]);
+      }
+
+      // ---- common reference, row-sum exchange, epilogue on this warp's D/2 columns ------------
+      const int last = n_blocks - 1;
+      float m_final = m_w;
+      if ((last & 1) != par) {
+        mbar_wait(ready_other, (last >> 1) & 1);
+        m_final = *m_other;
+      }
+      if (m_w != m_final) l *= fast_exp2((m_w - m_final) * scale_log2);
+      mbar_wait(&bars->o_full[t], 0);
+      tc_fence_after();
+      *l_mine = l;
+      tc_fence_before();
+      named_bar_sync_rt(pair_bar, 64);
+      tc_fence_after();
+      l += *l_other;
+      const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+      const int tile_row0 = q_row0 + t * BLOCK_M;
+      if (rows_valid == BLOCK_M) {
+        uint8_t* stage = smem + L::kQ + t * L::kQTileBytes;
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 32) {
+          uint32_t o[32];
+          HG_TMEM_LD32(o_addr + c0, o, 0);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            uint4 w;
+            w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+            w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+            w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+            w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+            const int chunk = (half * DH + c0 + c) >> 3;  // 16-byte chunk of the row
+            uint8_t* dst = stage + (chunk >> 3) * L::kQHalfBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = w;
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync_rt(9 + t, 2 * BLOCK_M);  // the eight warps of this tile
+        if (half == 0 && wq == 0 && lane == 0) {
+#pragma unroll
+          for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&tmap_o, stage + h * L::kQHalfBytes, head * D + h * 64, split * n_q_rows + tile_row0);
+          bulk_commit_and_wait();
+        }
+      } else {
+        const bool row_ok = row < rows_valid;
+        T* orow = out + ((int64_t)(tile_row0 + row) * hq + head) * D + half * DH;
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 32) {
+          uint32_t o[32];
+          HG_TMEM_LD32(o_addr + c0, o, 0);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+              uint4 w;
+              w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+              w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+              w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+              w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+              st_v4(orow + c0 + c, w);
+            }
+          }
+        }
+      }
+      if (half == 0 && row < rows_valid && lse != nullptr)
+        lse[(int64_t)(tile_row0 + row) * hq + head] = (l > 0.f) ? (m_final * scale_log2 + fast_log2(l)) * kLn2 : -INFINITY;
       tc_fence_before();
     }
   } else {
@@ -1125,7 +1332,7 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   const int tiles_per_group = (p.q_per_group + kTiles * BLOCK_M - 1) / (kTiles * BLOCK_M);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(p.n_groups * tiles_per_group * splits), (unsigned)p.hq, 1);
-  cfg.blockDim = dim3(kSplit == 1 ? kThreadsSplit : kThreads);
+  cfg.blockDim = dim3((kSplit == 1 || kSplit == 3) ? kThreadsSplit : kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -1142,7 +1349,7 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   return check_launch("prefix_attn_sm100");
 }
 
-#if !defined(HG_PREFIX_TU_CAUSAL) && !defined(HG_PREFIX_TU_SPLIT) && !defined(HG_PREFIX_TU_SIMPLE)
+#if !defined(HG_PREFIX_TU_CAUSAL) && !defined(HG_PREFIX_TU_SPLIT) && !defined(HG_PREFIX_TU_SIMPLE) && !defined(HG_PREFIX_TU_ALT)
 #ifdef HG_PREFIX_TRACE
 extern "C" int hg_debug_read_trace(long long* host_buf, int n) {
   cudaDeviceSynchronize();
@@ -1166,15 +1373,17 @@ int suggest_prefix_splits(int n_groups, int q_per_group, int hq, int max_k_len, 
 int launch_prefix_causal(const PrefixParams& p, int dtype, cudaStream_t s);  // prefix_sm100_causal.cu
 int launch_prefix_split(const PrefixParams& p, int dtype, cudaStream_t s);   // prefix_sm100_split.cu
 int launch_prefix_simple(const PrefixParams& p, int dtype, cudaStream_t s);  // prefix_sm100_simple.cu
+int launch_prefix_alt(const PrefixParams& p, int dtype, cudaStream_t s);     // prefix_sm100_alt.cu
 
-// HYDRAGEN_B200_PREFIX_SOFTMAX = base | split | simple (read once): which softmax organisation the non-causal
-// launches use (0 base: software pipelined, the default; 1 split-column; 2 simple: not pipelined)
+// HYDRAGEN_B200_PREFIX_SOFTMAX = base | split | simple | alt (read once): which softmax organisation the non-causal
+// launches use (0 base: software pipelined, the default; 1 split-column; 2 simple: not pipelined; 3 alternate-block)
 static int softmax_variant() {
   static const int v = [] {
     const char* e = getenv("HYDRAGEN_B200_PREFIX_SOFTMAX");
     if (e == nullptr) return HG_PREFIX_SOFTMAX_DEFAULT;
     if (e[0] == 's' && e[1] == 'p') return 1;
     if (e[0] == 's' && e[1] == 'i') return 2;
+    if (e[0] == 'a') return 3;
     return 0;
   }();
   return v;
@@ -1196,6 +1405,7 @@ int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
   }
   if (softmax_variant() == 1) return launch_prefix_split(p, dtype, s);
   if (softmax_variant() == 2) return launch_prefix_simple(p, dtype, s);
+  if (softmax_variant() == 3) return launch_prefix_alt(p, dtype, s);
   if (dtype == HG_BF16) {
     if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false, 0>(p, dtype, s);
     if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, false, 0>(p, dtype, s);
@@ -1213,6 +1423,17 @@ int launch_prefix_causal(const PrefixParams& p, int dtype, cudaStream_t s) {
   } else {
     if (p.d == 128) return launch_prefix_inst<__half, 128, true, 0>(p, dtype, s);
     if (p.d == 64) return launch_prefix_inst<__half, 64, true, 0>(p, dtype, s);
+  }
+  return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
+}
+#elif defined(HG_PREFIX_TU_ALT)  // fifth translation unit: the alternate-block softmax instantiations
+int launch_prefix_alt(const PrefixParams& p, int dtype, cudaStream_t s) {
+  if (dtype == HG_BF16) {
+    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false, 3>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, false, 3>(p, dtype, s);
+  } else {
+    if (p.d == 128) return launch_prefix_inst<__half, 128, false, 3>(p, dtype, s);
+    if (p.d == 64) return launch_prefix_inst<__half, 64, false, 3>(p, dtype, s);
   }
   return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
 }

@@ -240,11 +240,19 @@ def test_causal_prefill_full_size_property():
     assert (lse[:, hs].double().cpu() - rl).abs().max().item() < 5e-3
 
 
-@pytest.mark.parametrize("softmax", ["split"])
+_EXPERIMENTAL = os.environ.get("HYDRAGEN_B200_TEST_EXPERIMENTAL") == "1"
+
+
+@pytest.mark.parametrize("softmax", [
+    "split",
+    # 'simple' passed a hand-run parity check (profiles/r01s_*); 'alt' has not been run on hardware yet (written after
+    # the GPU budget of round 1 was spent): both are opt-in here until a GPU run has seen them pass inside pytest
+    pytest.param("simple", marks=pytest.mark.skipif(not _EXPERIMENTAL, reason="set HYDRAGEN_B200_TEST_EXPERIMENTAL=1")),
+    pytest.param("alt", marks=pytest.mark.skipif(not _EXPERIMENTAL, reason="set HYDRAGEN_B200_TEST_EXPERIMENTAL=1")),
+])
 def test_split_column_softmax_variant(softmax):
-    """The experimental split-column softmax organisation of the prefix kernel (HYDRAGEN_B200_PREFIX_SOFTMAX=split,
-    measured slower than the default and therefore off: DESIGN.md 4.1) stays correct: run in a subprocess because the
-    switch is read once per process."""
+    """The alternative softmax organisations of the prefix kernel (HYDRAGEN_B200_PREFIX_SOFTMAX=split | simple | alt; off
+    by default: DESIGN.md 4.1) stay correct: run in a subprocess because the switch is read once per process."""
     import subprocess
     import sys
 
