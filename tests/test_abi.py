@@ -157,3 +157,31 @@ def test_row_view_helpers_accept_fused_projection_views():
     cache = torch.zeros(3, 16, 2, 64)
     assert _rows_view(cache[:, :9]) is None                 # a cache prefix slice needs a copy ...
     assert _rows_view(cache[:1, :9]) == 128                 # ... unless it is one sequence
+
+
+def test_header_is_plain_c_and_links(built_lib, tmp_path):
+    """include/hydragen_b200.h compiles as C99 (no C++-isms, no torch types) and a C program linked against the
+    library can call the entry points that need no GPU."""
+    import shutil
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "hydragen_b200.h"\n'
+        "int main(void) {\n"
+        "  if (hg_abi_version() != HG_ABI_VERSION) return 1;\n"
+        "  if (hg_sm_count() != 0) return 2;                       /* hg_init not called */\n"
+        "  if (hg_combine_lse(0, 0, 0, 0, 0, 4, 64, HG_BF16, 0) != HG_ERR_INVALID_ARGUMENT) return 3;\n"
+        "  if (strstr(hg_last_error(), \"n = 0\") == 0) return 4;\n"
+        "  if (hg_prefix_suggest_splits(1, 1024, 4, 2048, HG_MAX_COMBINE) < 1) return 5;\n"
+        '  printf("abi %d ok\\n", hg_abi_version());\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(built_lib)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lhydragen_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "abi 1 ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
