@@ -16,5 +16,6 @@ HYDRAGEN_B200_PREFIX_SOFTMAX=alt run time_alt_1024 100 python scripts/time_prefi
 TP_B=4096 run time_base_4096 100 python scripts/time_prefix.py
 HYDRAGEN_B200_PREFIX_SOFTMAX=alt TP_B=4096 run time_alt_4096 100 python scripts/time_prefix.py
 HYDRAGEN_B200_PREFIX_SOFTMAX=alt TP_B=128 run time_alt_128 100 python scripts/time_prefix.py
+[ -x scripts/microbench/softmax_stream ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o scripts/microbench/softmax_stream scripts/microbench/softmax_stream.cu
 run softmax_stream 60 scripts/microbench/softmax_stream
 cat $S
