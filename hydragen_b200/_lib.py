@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 from typing import Optional, Sequence
 
 import torch
@@ -17,9 +17,18 @@ from . import build as _build
 
 HG_F16, HG_BF16, HG_F32 = 0, 1, 2
 HG_MAX_COMBINE = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
+MAX_PREFIX_LEVELS = 4
 
 _DTYPES = {torch.float16: HG_F16, torch.bfloat16: HG_BF16, torch.float32: HG_F32}
+
+class PrefixLevel(Structure):
+    """hg_prefix_level of include/hydragen_b200.h."""
+
+    _fields_ = [("k", c_void_p), ("v", c_void_p), ("out", c_void_p), ("lse", c_void_p), ("cu_seqlens_k", c_void_p),
+                ("n_k_rows", c_int64), ("kv_stride_row", c_int64), ("n_groups", c_int32), ("k_len", c_int32),
+                ("max_k_len", c_int32), ("reserved", c_int32)]
+
 
 # every symbol include/hydragen_b200.h declares: name -> (restype, argtypes)
 _c_void_pp = POINTER(c_void_p)
@@ -39,19 +48,19 @@ SYMBOLS = {
     "hg_prefix_attn_fwd": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
-         c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_void_p],
+         c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_void_p, c_int64, c_void_p],
     ),
-    "hg_prefix_attn_split_fwd": (
+    "hg_prefix_attn_grouped_fwd": (
         c_int,
-        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
-         c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_int, c_void_p],
+        [c_void_p, c_int64, c_int64, POINTER(PrefixLevel), c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_int64, c_void_p],
     ),
+    "hg_prefix_workspace_bytes": (c_int64, []),
+    "hg_prefix_schedule": (c_int, [POINTER(PrefixLevel), c_int, c_int64, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32)]),
     "hg_causal_attn_fwd": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64,
          c_float, c_int, c_void_p],
     ),
-    "hg_prefix_suggest_splits": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "hg_decode_attn_fused": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -72,6 +81,7 @@ SYMBOLS = {
 
 _lib: Optional[ctypes.CDLL] = None
 _inited_devices: set = set()
+_prefix_ws: dict = {}  # device index -> zero-initialised workspace of the persistent prefix kernel
 
 
 class HydragenB200Error(RuntimeError):
@@ -119,6 +129,22 @@ def ensure_init(device: torch.device):
     if idx not in _inited_devices:
         _check(load().hg_init(idx), "hg_init")
         _inited_devices.add(idx)
+    return idx
+
+
+def prefix_workspace(device: torch.device) -> torch.Tensor:
+    """The per-device workspace of the persistent prefix kernel (stream-K partials + flags): allocated and zeroed
+    once, then owned by the library's launches.  All prefix launches of a process on one device share it, so they must
+    be stream-ordered (they are: every caller in this package launches on the current stream).  Allocate your own
+    (``torch.zeros(hg_prefix_workspace_bytes)``) for launches that may overlap on different streams."""
+    idx = ensure_init(device)
+    ws = _prefix_ws.get(idx)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise HydragenB200Error("the prefix workspace must exist before CUDA-graph capture: run one eager step first")
+        ws = torch.zeros(int(load().hg_prefix_workspace_bytes()), dtype=torch.uint8, device=torch.device("cuda", idx))
+        _prefix_ws[idx] = ws
+    return ws
 
 
 def dtype_code(dt: torch.dtype) -> int:
@@ -181,21 +207,49 @@ def rowwise_attn_fwd(q, k, v, seq_lens, cu_seqlens_k, kv_group_size, causal, out
 
 
 def prefix_attn_fwd(q, k, v, out, lse, n_groups, q_per_group, n_k_rows, k_len, cu_seqlens_k, max_k_len,
-                    hq, hkv, d, q_stride_row, kv_stride_row, sm_scale, kv_splits: int = 1) -> None:
-    """out / lse hold kv_splits partial results back to back ([kv_splits, rows, hq, d] / [kv_splits, rows, hq])."""
+                    hq, hkv, d, q_stride_row, kv_stride_row, sm_scale, workspace: Optional[torch.Tensor] = None, split: bool = True) -> None:
+    """One shared level.  ``split=False`` keeps every (group, tile, head) unit on one CTA (no workspace)."""
     ensure_init(q.device)
+    ws = (workspace if workspace is not None else prefix_workspace(q.device)) if split else None
     with torch.cuda.device(q.device):
-        if kv_splits == 1:
-            rc = load().hg_prefix_attn_fwd(
-                _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), n_groups, q_per_group, n_k_rows, k_len,
-                _ptr(cu_seqlens_k), max_k_len, hq, hkv, d, q_stride_row, kv_stride_row, float(sm_scale),
-                dtype_code(q.dtype), _stream(q))
-        else:
-            rc = load().hg_prefix_attn_split_fwd(
-                _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), n_groups, q_per_group, n_k_rows, k_len,
-                _ptr(cu_seqlens_k), max_k_len, hq, hkv, d, q_stride_row, kv_stride_row, float(sm_scale),
-                dtype_code(q.dtype), kv_splits, _stream(q))
+        rc = load().hg_prefix_attn_fwd(
+            _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), n_groups, q_per_group, n_k_rows, k_len,
+            _ptr(cu_seqlens_k), max_k_len, hq, hkv, d, q_stride_row, kv_stride_row, float(sm_scale),
+            dtype_code(q.dtype), _ptr(ws), 0 if ws is None else ws.numel(), _stream(q))
     _check(rc, "hg_prefix_attn_fwd")
+
+
+def make_prefix_level(k, v, out, lse, cu_seqlens_k, n_k_rows, kv_stride_row, n_groups, k_len, max_k_len) -> PrefixLevel:
+    return PrefixLevel(k.data_ptr(), v.data_ptr(), out.data_ptr(), 0 if lse is None else lse.data_ptr(),
+                       0 if cu_seqlens_k is None else cu_seqlens_k.data_ptr(), n_k_rows, kv_stride_row, n_groups, k_len, max_k_len, 0)
+
+
+def prefix_attn_grouped_fwd(q, n_q_rows, q_stride_row, levels: Sequence[PrefixLevel], hq, hkv, d, sm_scale,
+                            workspace: Optional[torch.Tensor] = None, split: bool = True) -> None:
+    """Every shared level of a hierarchy in one persistent launch (hg_prefix_attn_grouped_fwd)."""
+    ensure_init(q.device)
+    ws = (workspace if workspace is not None else prefix_workspace(q.device)) if split else None
+    arr = (PrefixLevel * len(levels))(*levels)
+    with torch.cuda.device(q.device):
+        rc = load().hg_prefix_attn_grouped_fwd(_ptr(q), n_q_rows, q_stride_row, arr, len(levels), hq, hkv, d, float(sm_scale),
+                                               dtype_code(q.dtype), _ptr(ws), 0 if ws is None else ws.numel(), _stream(q))
+    _check(rc, "hg_prefix_attn_grouped_fwd")
+
+
+def prefix_schedule(levels, n_q_rows: int, hq: int, n_sms: int = 148, allow_split: bool = True):
+    """Host-side work schedule (no GPU needed).  ``levels``: list of (n_groups, k_len, max_k_len) with max_k_len > 0 for
+    ragged levels.  Returns (n_ctas, list of piece tuples (cta, unit, level, head, group, tile, b_lo, b_hi, split, slot))."""
+    arr = (PrefixLevel * len(levels))()
+    for a, (ng, kl, mk) in zip(arr, levels):
+        a.n_groups, a.k_len, a.max_k_len = ng, kl, mk
+    lib = load()
+    n_ctas = c_int32(0)
+    n = lib.hg_prefix_schedule(arr, len(levels), n_q_rows, hq, n_sms, int(allow_split), None, 0, ctypes.byref(n_ctas))
+    _check(min(n, 0), "hg_prefix_schedule")
+    buf = (c_int32 * (10 * max(1, n)))()
+    n2 = lib.hg_prefix_schedule(arr, len(levels), n_q_rows, hq, n_sms, int(allow_split), buf, n, ctypes.byref(n_ctas))
+    _check(min(n2, 0), "hg_prefix_schedule")
+    return int(n_ctas.value), [tuple(buf[i * 10 : i * 10 + 10]) for i in range(n2)]
 
 
 def causal_attn_fwd(q, k, v, out, lse, b, sq, sk, hq, hkv, d, q_stride_row, kv_stride_row, sm_scale) -> None:
@@ -204,11 +258,6 @@ def causal_attn_fwd(q, k, v, out, lse, b, sq, sk, hq, hkv, d, q_stride_row, kv_s
         rc = load().hg_causal_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), b, sq, sk, hq, hkv, d, q_stride_row,
                                        kv_stride_row, float(sm_scale), dtype_code(q.dtype), _stream(q))
     _check(rc, "hg_causal_attn_fwd")
-
-
-def prefix_suggest_splits(device, n_groups: int, q_per_group: int, hq: int, max_k_len: int, max_splits: int) -> int:
-    ensure_init(device)
-    return int(load().hg_prefix_suggest_splits(n_groups, q_per_group, hq, max_k_len, max_splits))
 
 
 def kv_append(k_new, v_new, positions, k_cache, v_cache) -> None:

@@ -2,8 +2,8 @@
 (same function names, argument meaning, return layouts and error behaviour), running on the
 hand-written sm_100a kernels behind the C ABI.
 
-Launches per call with L shared levels:  L tcgen05 prefix launches + 1 row-wise launch that does
-the suffix branch AND the (L+1)-way combine -- versus, in the reference, L flash-attn launches +
+Launches per call with L shared levels:  ONE persistent tcgen05 prefix launch over all L levels + 1 row-wise launch
+that does the suffix branch AND the (L+1)-way combine -- versus, in the reference, L flash-attn launches +
 L LSE transposes + cast + split-K + reduce + combine (Triton for 2 inputs, ~8 eager torch
 launches otherwise; hydragen/attention.py:246-352, hydragen/flash.py:163-281).
 """
@@ -22,6 +22,7 @@ from .flash import (
     flash_attention_seqlen,
     flash_attention_varlen,
     prefix_attention_grouped,
+    prefix_attention_levels,
     prefix_attention_partials,
     suffix_attention_fused,
 )
@@ -118,22 +119,18 @@ def hydragen_attention(
         assert sk.shape == sv.shape, f"{sk.shape} {sv.shape}"
 
     b, nq, hq, d = q.shape
-    outs, lses = [], []
-    early = k.shape[1] == 0 and len(shared_ks) == 1
-    max_splits = 1 if early else max(1, _lib.HG_MAX_COMBINE // max(1, len(shared_ks)))
-    for sk, sv, scu, smax, use_varlen in zip(shared_ks, shared_vs, shared_cu_seq_lens, shared_max_seq_lens, use_varlens):
-        if not use_varlen:
-            n = sk.shape[0]
-            assert b % n == 0, f"{b} {n}"
-            so, sl = prefix_attention_partials(q, sk, sv, n_groups=n, max_splits=max_splits)
-        else:
-            n = scu.shape[0] - 1
-            assert b % n == 0, f"{b} {n}"
-            so, sl = prefix_attention_partials(q, sk, sv, n_groups=n, cu_seqlens_k=scu, max_seqlen_k=smax, max_splits=max_splits)
-        if early:
-            return so[0]  # attention.py:273-274, 330-331
-        outs += so
-        lses += sl
+    n_groups = []
+    for sk, scu, use_varlen in zip(shared_ks, shared_cu_seq_lens, use_varlens):
+        n = scu.shape[0] - 1 if use_varlen else sk.shape[0]
+        assert b % n == 0, f"{b} {n}"
+        n_groups.append(n)
+    # every shared level in ONE persistent launch (the reference loops: one flash-attn call + LSE transpose per level)
+    outs, lses = prefix_attention_levels(
+        q, shared_ks, shared_vs, n_groups,
+        [scu if uv else None for scu, uv in zip(shared_cu_seq_lens, use_varlens)],
+        [smax if uv else None for smax, uv in zip(shared_max_seq_lens, use_varlens)])
+    if k.shape[1] == 0 and len(shared_ks) == 1:
+        return outs[0]  # attention.py:273-274, 330-331
 
     if k.shape[1] == 0:
         # >= 2 shared levels and no unique keys: undefined in the reference (flash-attn with
@@ -160,7 +157,7 @@ def hydragen_attention_decode(
 ):
     """A whole decode step of Hydragen attention for one layer: what the reference's DECODE branch does
     with ``update_per_completion_kvs`` followed by ``hydragen_attention(..., seq_lens=pos + 1)``
-    (hydragen/llama.py:564-587), in ``len(shared_ks) + 1`` launches: one tcgen05 prefix launch per shared
+    (hydragen/llama.py:564-587), in TWO launches: one persistent tcgen05 prefix launch over every shared
     level, then ONE launch that appends the new token's K/V at ``positions[b]``, runs the suffix branch over
     the sequence's ``positions[b] + 1`` own keys and merges every partial result.  The caches are updated
     in place; returns ``out [b, 1, hq, d]``."""
@@ -171,20 +168,16 @@ def hydragen_attention_decode(
     assert q.ndim == 4 and q.shape[1] == 1, f"{q.shape}"
     assert len(shared_vs) == n and len(shared_cu_seq_lens) == n and len(shared_max_seq_lens) == n and len(use_varlens) == n
     b = q.shape[0]
-    outs, lses = [], []
-    max_splits = max(1, _lib.HG_MAX_COMBINE // max(1, n))
-    for sk, sv, scu, smax, use_varlen in zip(shared_ks, shared_vs, shared_cu_seq_lens, shared_max_seq_lens, use_varlens):
+    n_groups = []
+    for sk, sv, scu, use_varlen in zip(shared_ks, shared_vs, shared_cu_seq_lens, use_varlens):
         assert sk.shape == sv.shape, f"{sk.shape} {sv.shape}"
-        if not use_varlen:
-            ng = sk.shape[0]
-            assert b % ng == 0, f"{b} {ng}"
-            so, sl = prefix_attention_partials(q, sk, sv, n_groups=ng, max_splits=max_splits)
-        else:
-            ng = scu.shape[0] - 1
-            assert b % ng == 0, f"{b} {ng}"
-            so, sl = prefix_attention_partials(q, sk, sv, n_groups=ng, cu_seqlens_k=scu, max_seqlen_k=smax, max_splits=max_splits)
-        outs += so
-        lses += sl
+        ng = scu.shape[0] - 1 if use_varlen else sk.shape[0]
+        assert b % ng == 0, f"{b} {ng}"
+        n_groups.append(ng)
+    outs, lses = prefix_attention_levels(
+        q, shared_ks, shared_vs, n_groups,
+        [scu if uv else None for scu, uv in zip(shared_cu_seq_lens, use_varlens)],
+        [smax if uv else None for smax, uv in zip(shared_max_seq_lens, use_varlens)])
     out, _ = decode_attention_fused(q, k_new, v_new, positions, k_cache, v_cache, outs, lses)
     return out
 

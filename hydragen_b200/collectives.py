@@ -18,7 +18,7 @@ from . import _lib
 
 
 class MultimemAllReduce:
-    def __init__(self, nbytes: int, device: torch.device, group=None, n_blocks: int = 128):
+    def __init__(self, nbytes: int, device: torch.device, group=None, n_blocks: int = 32):
         """Collective over ``group`` (default: world) for messages carved out of one symmetric arena of ``nbytes``."""
         import torch.distributed._symmetric_memory as symm_mem
 
@@ -29,7 +29,8 @@ class MultimemAllReduce:
         name = self.group.group_name
         self.arena = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
         self._h = symm_mem.rendezvous(self.arena, name)
-        self.flags = symm_mem.empty(n_blocks * self.world, dtype=torch.int32, device=device)
+        # flag words of csrc/allreduce.cu: [0] epoch, [1] CTA count, [32 + p] / [64 + p] per-peer arrival epochs
+        self.flags = symm_mem.empty(128, dtype=torch.int32, device=device)
         self.flags.zero_()
         self._hf = symm_mem.rendezvous(self.flags, name)
         self.mc_base = int(self._h.multicast_ptr or 0)  # 0: no multicast mapping on this platform
@@ -77,9 +78,17 @@ class MultimemAllReduce:
 
 
 def make_all_reduce(nbytes: int, device: torch.device, group=None) -> Optional[MultimemAllReduce]:
-    """The NVLS collective if this process group / platform supports it, else None (caller falls back to NCCL)."""
+    """The NVLS collective if EVERY rank of the group could set it up, else None on every rank (the caller then uses
+    NCCL).  Collective: all ranks must call it together.  The ranks agree on the outcome -- a rank that fell back on
+    its own would leave the others spinning in the kernel's cross-rank flags."""
+    ar, ok = None, 0
     try:
         ar = MultimemAllReduce(nbytes, device, group)
-        return ar if ar.available else None
-    except Exception:
-        return None
+        ok = 1 if ar.available else 0
+    except Exception as ex:
+        import warnings
+
+        warnings.warn(f"NVLS all-reduce unavailable on this rank ({ex!r}); the group will agree on NCCL")
+    flag = torch.tensor([ok], device=device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return ar if int(flag.item()) == 1 else None

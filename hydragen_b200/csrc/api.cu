@@ -7,6 +7,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "prefix_sched.h"
 
 namespace hg {
 
@@ -179,47 +180,115 @@ int hg_decode_attn_fused(const void* q, const void* k_new, const void* v_new, co
   return launch_rowwise(p, dtype, (cudaStream_t)stream);
 }
 
-int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int n_groups, int q_per_group,
-                       int64_t n_k_rows, int k_len, const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
-                       int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype, void* stream) {
-  return hg_prefix_attn_split_fwd(q, k, v, out, lse, n_groups, q_per_group, n_k_rows, k_len, cu_seqlens_k, max_k_len, hq, hkv, d,
-                                  q_stride_row, kv_stride_row, sm_scale, dtype, 1, stream);
+static int fill_prefix_levels(PrefixParams& p, const hg_prefix_level* levels_host, int n_levels, const char* who) {
+  if (n_levels < 1 || n_levels > kMaxLevels) return set_error(HG_ERR_INVALID_ARGUMENT, "%s: %d shared levels (1..%d)", who, n_levels, kMaxLevels);
+  if (levels_host == nullptr) return set_error(HG_ERR_INVALID_ARGUMENT, "%s: null level table", who);
+  p.n_levels = n_levels;
+  for (int l = 0; l < n_levels; ++l) {
+    const hg_prefix_level& h = levels_host[l];
+    if (h.n_groups < 1 || h.n_k_rows < 0 || h.k_len < 0 || h.max_k_len < 0)
+      return set_error(HG_ERR_INVALID_ARGUMENT, "%s: level %d: bad sizes n_groups=%d n_k_rows=%lld k_len=%d max_k_len=%d", who, l, h.n_groups,
+                       (long long)h.n_k_rows, h.k_len, h.max_k_len);
+    if (p.n_q_rows % h.n_groups != 0)
+      return set_error(HG_ERR_INVALID_ARGUMENT, "%s: level %d: %d groups do not divide %lld query rows", who, l, h.n_groups, (long long)p.n_q_rows);
+    if (h.cu_seqlens_k == nullptr && (int64_t)h.n_groups * h.k_len > h.n_k_rows)
+      return set_error(HG_ERR_INVALID_ARGUMENT, "%s: level %d: n_groups * k_len (%d * %d) exceeds n_k_rows (%lld)", who, l, h.n_groups, h.k_len,
+                       (long long)h.n_k_rows);
+    if (p.n_q_rows > 0 && (h.k == nullptr || h.v == nullptr || h.out == nullptr))
+      return set_error(HG_ERR_INVALID_ARGUMENT, "%s: level %d: null tensor pointer", who, l);
+    if (h.n_k_rows > 0x7fffffffLL) return set_error(HG_ERR_UNSUPPORTED, "%s: row counts must fit int32", who);
+    PrefixLevel& d = p.levels[l];
+    d.k = h.k; d.v = h.v; d.out = h.out; d.lse = h.lse;
+    d.cu_seqlens_k = h.cu_seqlens_k;
+    d.n_k_rows = h.n_k_rows; d.kv_stride_row = h.kv_stride_row;
+    d.n_groups = h.n_groups; d.k_len = h.k_len;
+    d.max_k_len = h.cu_seqlens_k != nullptr ? (h.max_k_len > 0 ? h.max_k_len : (int)h.n_k_rows) : h.k_len;
+  }
+  return HG_OK;
 }
 
-int hg_prefix_suggest_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits) {
-  if (n_groups < 1 || q_per_group < 1 || hq < 1 || max_k_len < 1 || max_splits < 1) return 1;
-  return suggest_prefix_splits(n_groups, q_per_group, hq, max_k_len, max_splits > HG_MAX_COMBINE ? HG_MAX_COMBINE : max_splits);
-}
+int64_t hg_prefix_workspace_bytes(void) { return prefix_workspace_bytes(); }
 
-int hg_prefix_attn_split_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int n_groups, int q_per_group,
-                             int64_t n_k_rows, int k_len, const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
-                             int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype, int kv_splits, void* stream) {
-  if (kv_splits < 1 || kv_splits > HG_MAX_COMBINE)
-    return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: kv_splits = %d outside [1, %d]", kv_splits, HG_MAX_COMBINE);
+int hg_prefix_attn_grouped_fwd(const void* q, int64_t n_q_rows, int64_t q_stride_row, const hg_prefix_level* levels_host, int n_levels,
+                               int hq, int hkv, int d, float sm_scale, int dtype, void* workspace, int64_t workspace_bytes,
+                               void* stream) {
   if (!g_info.ready) return set_error(HG_ERR_NOT_INITIALIZED, "prefix: hg_init() has not been called");
-  if (n_groups < 0 || q_per_group < 0 || n_k_rows < 0 || hq < 1 || hkv < 1)
-    return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: bad sizes n_groups=%d q_per_group=%d n_k_rows=%lld hq=%d hkv=%d", n_groups,
-                     q_per_group, (long long)n_k_rows, hq, hkv);
+  if (n_q_rows < 0 || hq < 1 || hkv < 1) return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: bad sizes n_q_rows=%lld hq=%d hkv=%d", (long long)n_q_rows, hq, hkv);
   if (hq % hkv != 0) return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: hq (%d) must be a multiple of hkv (%d)", hq, hkv);
-  if (cu_seqlens_k == nullptr && (k_len < 0 || (int64_t)n_groups * k_len > n_k_rows))
-    return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: n_groups * k_len (%d * %d) exceeds n_k_rows (%lld)", n_groups, k_len,
-                     (long long)n_k_rows);
-  if (n_groups > 0 && q_per_group > 0 && (q == nullptr || out == nullptr || k == nullptr || v == nullptr))
-    return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: null tensor pointer");
-  if ((int64_t)n_groups * q_per_group * kv_splits > 0x7fffffffLL || n_k_rows > 0x7fffffffLL)
-    return set_error(HG_ERR_UNSUPPORTED, "prefix: row counts must fit int32");
-  (void)max_k_len;
+  if (n_q_rows > 0 && q == nullptr) return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: null tensor pointer");
+  if (n_q_rows > 0x7fffffffLL) return set_error(HG_ERR_UNSUPPORTED, "prefix: row counts must fit int32");
+  if (hq > 65535) return set_error(HG_ERR_UNSUPPORTED, "prefix: hq > 65535");
+  if (workspace != nullptr && reinterpret_cast<uintptr_t>(workspace) % 16 != 0)
+    return set_error(HG_ERR_UNSUPPORTED, "prefix: the workspace must be 16-byte aligned");
   PrefixParams p;
   memset(&p, 0, sizeof(p));
-  p.q = q; p.k = k; p.v = v; p.out = out; p.lse = lse;
-  p.n_groups = n_groups; p.q_per_group = q_per_group;
-  p.n_k_rows = n_k_rows; p.k_len = k_len;
-  p.cu_seqlens_k = cu_seqlens_k; p.max_k_len = max_k_len;
+  p.q = q; p.n_q_rows = n_q_rows; p.q_stride_row = q_stride_row;
   p.hq = hq; p.hkv = hkv; p.d = d;
-  p.q_stride_row = q_stride_row; p.kv_stride_row = kv_stride_row;
   p.scale_log2 = sm_scale * kLog2e;
-  p.kv_splits = kv_splits;
+  p.workspace = workspace; p.workspace_bytes = workspace_bytes;
+  int rc = fill_prefix_levels(p, levels_host, n_levels, "prefix");
+  if (rc != HG_OK) return rc;
   return launch_prefix(p, dtype, (cudaStream_t)stream);
+}
+
+int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int n_groups, int q_per_group,
+                       int64_t n_k_rows, int k_len, const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
+                       int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+  if (n_groups < 0 || q_per_group < 0) return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: bad sizes n_groups=%d q_per_group=%d", n_groups, q_per_group);
+  if (n_groups == 0 || q_per_group == 0) return HG_OK;
+  hg_prefix_level lv;
+  memset(&lv, 0, sizeof(lv));
+  lv.k = k; lv.v = v; lv.out = out; lv.lse = lse; lv.cu_seqlens_k = cu_seqlens_k;
+  lv.n_k_rows = n_k_rows; lv.kv_stride_row = kv_stride_row;
+  lv.n_groups = n_groups; lv.k_len = k_len; lv.max_k_len = max_k_len;
+  return hg_prefix_attn_grouped_fwd(q, (int64_t)n_groups * q_per_group, q_stride_row, &lv, 1, hq, hkv, d, sm_scale, dtype, workspace,
+                                    workspace_bytes, stream);
+}
+
+int hg_prefix_schedule(const hg_prefix_level* levels_host, int n_levels, int64_t n_q_rows, int hq, int n_sms, int allow_split,
+                       int32_t* pieces_out, int max_pieces, int32_t* n_ctas_out) {
+  PrefixParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_q_rows = n_q_rows; p.hq = hq; p.hkv = hq; p.d = 128;
+  // the schedule depends on sizes only: pointers may be null here
+  if (n_levels < 1 || n_levels > kMaxLevels || levels_host == nullptr) return set_error(HG_ERR_INVALID_ARGUMENT, "prefix_schedule: %d levels", n_levels);
+  if (hq < 1 || n_q_rows < 1 || n_sms < 1) return set_error(HG_ERR_INVALID_ARGUMENT, "prefix_schedule: bad sizes");
+  p.n_levels = n_levels;
+  for (int l = 0; l < n_levels; ++l) {
+    const hg_prefix_level& h = levels_host[l];
+    PrefixLevel& d = p.levels[l];
+    d.n_groups = h.n_groups; d.k_len = h.k_len;
+    d.max_k_len = h.max_k_len > 0 ? h.max_k_len : h.k_len;
+    d.cu_seqlens_k = h.max_k_len > 0 ? reinterpret_cast<const int32_t*>(&d) : nullptr;  // non-null = "ragged level: cost from max_k_len"
+  }
+  SchedParams S;
+  int rc = build_prefix_schedule(p, n_sms, allow_split != 0, &S);
+  if (rc != HG_OK) return rc;
+  if (n_ctas_out != nullptr) *n_ctas_out = S.n_ctas;
+  int n = 0;
+  for (int c = 0; c < S.n_ctas; ++c) {
+    SchedIter it;
+    SchedPiece sp;
+    sched_begin(S, c, it);
+    while (sched_next(S, it, sp)) {
+      if (pieces_out != nullptr && n < max_pieces) {
+        int32_t* o = pieces_out + (int64_t)n * 10;
+        o[0] = c; o[1] = sp.unit; o[2] = sp.level; o[3] = sp.head; o[4] = sp.grp; o[5] = sp.mt;
+        o[6] = sp.b_lo; o[7] = sp.b_hi; o[8] = sp.split; o[9] = sp.slot;
+      }
+      if (sp.split) {  // cross-check the merge's view of the unit: this CTA must appear there with the same slot
+        int ctas[kMaxUnitPieces], slots[kMaxUnitPieces];
+        const int k = sched_unit_pieces(S, sp.unit, c, ctas, slots);
+        bool found = false;
+        for (int i = 0; i < k && i < kMaxUnitPieces; ++i) found = found || (ctas[i] == c && slots[i] == sp.slot);
+        if (!found || k > kMaxUnitPieces)
+          return set_error(HG_ERR_CUDA, "prefix_schedule: inconsistent piece table (unit %d, cta %d, %d pieces)", sp.unit, c, k);
+      }
+      ++n;
+    }
+  }
+  return n;
 }
 
 int hg_causal_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int b, int sq, int sk, int hq, int hkv,
@@ -233,15 +302,17 @@ int hg_causal_attn_fwd(const void* q, const void* k, const void* v, void* out, f
     return set_error(HG_ERR_INVALID_ARGUMENT, "causal_attn: null tensor pointer");
   if ((int64_t)b * sq > 0x7fffffffLL || (int64_t)b * sk > 0x7fffffffLL)
     return set_error(HG_ERR_UNSUPPORTED, "causal_attn: row counts must fit int32");
+  if (b == 0 || sq == 0) return HG_OK;
   PrefixParams p;
   memset(&p, 0, sizeof(p));
-  p.q = q; p.k = k; p.v = v; p.out = out; p.lse = lse;
-  p.n_groups = b; p.q_per_group = sq;
-  p.n_k_rows = (int64_t)b * sk; p.k_len = sk; p.max_k_len = sk;
+  p.q = q; p.n_q_rows = (int64_t)b * sq; p.q_stride_row = q_stride_row;
+  p.n_levels = 1;
+  PrefixLevel& lv = p.levels[0];
+  lv.k = k; lv.v = v; lv.out = out; lv.lse = lse;
+  lv.n_k_rows = (int64_t)b * sk; lv.kv_stride_row = kv_stride_row;
+  lv.n_groups = b; lv.k_len = sk; lv.max_k_len = sk;
   p.hq = hq; p.hkv = hkv; p.d = d;
-  p.q_stride_row = q_stride_row; p.kv_stride_row = kv_stride_row;
   p.scale_log2 = sm_scale * kLog2e;
-  p.kv_splits = 1;
   p.causal = 1;
   return launch_prefix(p, dtype, (cudaStream_t)stream);
 }

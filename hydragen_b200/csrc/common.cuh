@@ -164,25 +164,31 @@ struct RowwiseParams {
 };
 int launch_rowwise(const RowwiseParams& p, int dtype, cudaStream_t s);
 
-struct PrefixParams {
-  const void* q;
+// One shared level of a hierarchy: its K/V, its (partial) output, its grouping of the query rows.
+struct PrefixLevel {
   const void* k;
   const void* v;
   void* out;
   float* lse;
-  int n_groups, q_per_group;
-  int64_t n_k_rows;
-  int k_len;
   const int32_t* cu_seqlens_k;
-  int max_k_len;
-  int hq, hkv, d;
-  int64_t q_stride_row, kv_stride_row;
-  float scale_log2;
-  int kv_splits;  // >= 1; out / lse then hold kv_splits partial results back to back
-  int causal;     // bottom-right aligned causal mask inside every group (prefill): row r sees keys <= r + (k_len - q_per_group)
+  int64_t n_k_rows, kv_stride_row;
+  int n_groups, k_len, max_k_len;
 };
+struct PrefixParams {
+  const void* q;
+  int64_t n_q_rows, q_stride_row;
+  PrefixLevel levels[4];
+  int n_levels;
+  int hq, hkv, d;
+  float scale_log2;
+  int causal;  // one level, bottom-right aligned causal mask inside every group (prefill): row r sees keys <= r + (k_len - q_per_group)
+  void* workspace;  // stream-K partials and flags (hg_prefix_workspace_bytes); nullptr: whole units only
+  int64_t workspace_bytes;
+};
+struct SchedParams;
 int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s);
-int suggest_prefix_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits);
+int build_prefix_schedule(const PrefixParams& p, int n_sms, bool allow_split, SchedParams* out);
+int64_t prefix_workspace_bytes();
 
 int launch_allreduce_multimem(void* mc_ptr, void* out, const void* flags_dev, int rank, int world, int64_t nbytes, int dtype,
                               int n_blocks, cudaStream_t s);

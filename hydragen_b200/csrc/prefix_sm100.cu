@@ -1,62 +1,60 @@
-// Shared-prefix attention on the Blackwell tensor cores: tcgen05.mma + TMEM + TMA (sm_100a).
+// Shared-prefix attention on the Blackwell tensor cores: tcgen05.mma + TMEM + TMA (sm_100a), as ONE persistent
+// launch over every shared level of a hierarchy.
 //
-// Replaces the reference's prefix branch -- hydragen/attention.py:261-338 calling
-// flash_attention / flash_attention_varlen (hydragen/flash.py:284-351), i.e. flash-attn v2.3.6's
-// mma.sync (Ampere) kernel, plus the LSE transposes of attention.py:276-280,333-338.
+// Replaces the reference's prefix branch -- hydragen/attention.py:250-341, one flash_attention /
+// flash_attention_varlen call per shared level (hydragen/flash.py:284-351, i.e. flash-attn v2.3.6's mma.sync
+// kernel) plus the LSE transposes of attention.py:276-280,333-338.
 //
-// Inter-sequence batching makes this a dense problem: for one (group, head) the queries of every
-// sequence sharing the prefix form Q[q_per_group x d] and are multiplied against the single
-// K,V[k_len x d] of that prefix.  One CTA owns TWO 128-row Q tiles (A, B) of one head and streams
-// the prefix in 64-key blocks; every K/V block fetched feeds 256 query rows, and the score block of
-// each tile is double buffered in TMEM so that Q K^T runs two blocks ahead of the softmax:
+// Inter-sequence batching makes this a dense problem: for one (level, group, head) the queries of every sequence
+// sharing the prefix form Q[q_per_group x d] and are multiplied against the single K,V[k_len x d] of that prefix.
+// A UNIT of work is one (level, group, pair of 128-row Q tiles, head); the launch is a grid of persistent CTAs (one
+// per SM) that walk a stream-K schedule over all units of all levels (prefix_sched.h): a CTA gets a contiguous
+// range of the (unit, key block) space, so a unit may be split into PIECES handled by different CTAs.  Every piece
+// of a split unit leaves its unnormalised fp32 accumulator, running max and row sum in the workspace; when a CTA has
+// finished its range it merges, for every split unit it took part in, its share of the rows (all pieces end at about
+// the same time, so nobody waits long) and writes the final rows.  Whole units write their rows directly.
+//
+// Inside a piece (unchanged from round 1): the CTA streams the keys in 64-key blocks; every K/V block fetched feeds
+// 256 query rows, and the score block of each tile is double buffered in TMEM so that Q K^T runs two blocks ahead of
+// the softmax:
 //
 //   TMEM (512 columns)  S_A[0] S_A[1] S_B[0] S_B[1] (64 fp32 columns each) | O_A | O_B (128 each);
 //                       P_t(j) (16-bit) is written back over the first 32 columns of its S buffer
-//   warp 0 (1 lane)  TMA producer: Q_A, Q_B once, then a 4-deep ring whose slot u holds what MMA
-//                    iteration u consumes: V_u and K_{u+2} (cp.async.bulk.tensor, SWIZZLE_128B boxes)
-//   warps 1, 3       MMA issuer of tile A / B (all lanes walk the loop so descriptors stay in uniform
-//                    registers; one elected lane issues).  Per key block j:  PV_t(j)  QK_t(j+2)
-//                      S_t = Q_t K_j^T  (SS form, both operands K-major in smem, 128x64x16 per
-//                                        instruction, fp32 accumulate in TMEM)
-//                      O_t += P_t V_j   (TS form: P_t read from TMEM as the A operand, V_j straight
-//                                        from its row-major smem tile as an MN-major B operand --
-//                                        no transpose pass)
+//   warp 0 (1 lane)  TMA producer: per piece Q_A, Q_B, then a 4-deep ring whose slot u holds what MMA iteration u
+//                    consumes: V_u and K_{u+2} (cp.async.bulk.tensor, SWIZZLE_128B boxes)
+//   warps 1, 3       MMA issuer of tile A / B (all lanes walk the loop so descriptors stay in uniform registers; one
+//                    elected lane issues).  Per key block j:  PV_t(j)  QK_t(j+2)
+//                      S_t = Q_t K_j^T  (SS form, both operands K-major in smem, 128x64x16 per instruction)
+//                      O_t += P_t V_j   (TS form: P_t read from TMEM as the A operand, V_j straight from its
+//                                        row-major smem tile as an MN-major B operand -- no transpose pass)
 //   warp 2           TMEM allocator
-//   warps 4-7        softmax of tile A, warps 8-11 softmax of tile B: thread t owns row t
-//                    (tcgen05.ld 32x32b: lane == row, so the row max / row sum need no shuffles);
-//                    software pipelined: the scores of block j+1 are fetched and reduced to their
-//                    row max behind the MUFU exp2 requests of block j; scale / subtract / row sums as
-//                    packed fp32x2; P_t stored to TMEM as packed 16-bit; lazy rescale of O_t (only
-//                    when the running max grows by more than 2^8); epilogue O_t / l -> swizzled
-//                    smem (the dead Q_t tile) -> TMA store; LSE written directly in [b, nq, hq].
+//   warps 4-7        softmax of tile A, warps 8-11 softmax of tile B: thread t owns row t (tcgen05.ld 32x32b: lane ==
+//                    row, so the row max / row sum need no shuffles); software pipelined: the scores of block j+1
+//                    are fetched and reduced to their row max behind the MUFU exp2 requests of block j; scale /
+//                    subtract / row sums as packed fp32x2; lazy rescale of O_t (only when the running max grows by
+//                    more than 2^8); epilogue of a whole unit: O_t / l -> swizzled smem (the dead Q_t tile) -> TMA
+//                    store, LSE written directly in [b, nq, hq].
 //                    setmaxnreg: 56 registers for warps 0-3, 224 for the softmax warps (no spills in the loop)
 //
-// All producer/consumer edges are mbarriers (TMA complete_tx, tcgen05.commit, thread arrives); there
-// is no __syncthreads in the main loop.  Split-KV (kv_splits > 1): the CTAs of one tile each take a
-// contiguous range of key blocks and write their own partial (out, lse).
+// All producer/consumer edges are mbarriers with phases counted across pieces (TMA complete_tx, tcgen05.commit,
+// thread arrives); there is no __syncthreads between set-up and teardown.
 //
-// Instantiations (one translation unit each, compiled in parallel: this file is also #included by
-// prefix_sm100_causal.cu and prefix_sm100_split.cu):
-//   <T, D, kCausal = false, kSplit = 0>  the decode hot path (hg_prefix_attn_fwd / _split_fwd)
-//   <T, D, kCausal = true,  kSplit = 0>  prefill: bottom-right aligned causal mask inside every group
-//                                        (hg_causal_attn_fwd): row tiles heavy-first, only the visible key
-//                                        blocks are streamed, masks only in the blocks crossing the diagonal
-//   <T, D, kCausal = false, kSplit = 1>  experimental split-column softmax (two warpgroups per tile); measured
-//                                        slower, selected only by HYDRAGEN_B200_PREFIX_SOFTMAX=split
-//   <T, D, kCausal = false, kSplit = 2>  experimental non-pipelined softmax loop (prefix_sm100_simple.cu),
-//                                        HYDRAGEN_B200_PREFIX_SOFTMAX=simple
-//   <T, D, kCausal = false, kSplit = 3>  alternate-block softmax: four softmax warps per sub-partition without a
-//                                        per-block exchange (prefix_sm100_alt.cu, HYDRAGEN_B200_PREFIX_SOFTMAX=alt);
-//                                        written after the GPU budget of round 1 was spent: NOT yet run on hardware
+// Instantiations: <T, D, kCausal = false> the decode hot path (hg_prefix_attn_fwd / hg_prefix_attn_grouped_fwd);
+// <T, D, kCausal = true> prefill (hg_causal_attn_fwd, second translation unit prefix_sm100_causal.cu): bottom-right
+// aligned causal mask inside every group, whole units only, heavy row tiles first, only the visible key blocks are
+// streamed, masks only in the blocks crossing the diagonal.
 //
-// Algorithmic work per CTA: 4 * rows * k_len * d FLOP.  Bound: tensor pipe (AI ~ 680 FLOP/B at the
-// 7B config), with the MUFU exp2 rate (16/clk/SM == the 128x128x128 MMA rate) the co-limiter.
+// Algorithmic work per unit: 4 * rows * k_len * d FLOP.  Bound: tensor pipe (AI ~ 680 FLOP/B at the 7B config), with
+// the MUFU exp2 rate (16/clk/SM == the 128x128x128 MMA rate) the co-limiter.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "common.cuh"
+#include "prefix_sched.h"
 
 namespace hg {
 
@@ -64,25 +62,25 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 64;   // keys per block: S_t block = 64 TMEM columns, double buffered
-constexpr int kTiles = 2;  // Q tiles per CTA (ping-pong)
-constexpr int kThreads = 384;       // base: TMA / MMA warpgroup + one softmax warpgroup per tile
-constexpr int kThreadsSplit = 640;  // split-column softmax: two softmax warpgroups per tile
+constexpr int kTiles = 2;     // Q tiles per unit (ping-pong)
+constexpr int kThreads = 384;  // TMA / MMA warpgroup + one softmax warpgroup per tile
 constexpr uint32_t kTmemCols = 512;
 __host__ __device__ constexpr uint32_t tmem_s(int t, int b) { return (uint32_t)t * 128u + (uint32_t)b * 64u; }  // S_t buffer b (P aliases its first 32 columns)
 __host__ __device__ constexpr uint32_t tmem_o(int t) { return 256u + (uint32_t)t * 128u; }                       // O_t
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-#ifndef HG_PREFIX_SOFTMAX_DEFAULT
-#define HG_PREFIX_SOFTMAX_DEFAULT 0  // softmax organisation used when HYDRAGEN_B200_PREFIX_SOFTMAX is not set (0 base)
-#endif
-#ifndef HG_PREFIX_BDELAY_DEFAULT
-#define HG_PREFIX_BDELAY_DEFAULT 700  // cycles tile B's softmax starts after tile A's (0: together); long prefixes only
-#endif
-#ifndef HG_PREFIX_EMU_EVERY
-#define HG_PREFIX_EMU_EVERY 0
-#endif
-// every n-th pair of exponentials is computed on the FMA pipes instead of MUFU (0: none).  Measured at cfg#2
-// (B200, graph-timed): 0 -> 35.1 us, 4 -> 36.1, 3 -> 36.0, 2 -> 36.2: the warps are issue-bound, not MUFU-bound.
-constexpr int kEmuEvery = HG_PREFIX_EMU_EVERY;
+
+// ---- workspace (caller-owned, zero-initialised once; see hg_prefix_workspace_bytes) ----------------------
+constexpr int kMaxCtas = 160;             // >= SMs of the device (148)
+constexpr int kWsWordEpoch = 0;           // launches completed on this workspace
+constexpr int kWsWordExit = 1;            // CTAs of the running launch that are done
+constexpr int kWsWordFlags = 32;          // flag (cta, slot, tile) = word 32 + (cta * 2 + slot) * 2 + tile
+constexpr int kWsFlagBytes = 4096;        // >= (32 + 4 * kMaxCtas) * 4
+// one slot = the partial result of one piece: per tile, O as [16-byte chunk][row][4 floats] (a warp whose lanes are
+// consecutive rows reads / writes 512 contiguous bytes), then (max in log2 units, row sum) per row
+__host__ __device__ constexpr int64_t ws_slot_floats(int d) { return (int64_t)kTiles * BLOCK_M * (d + 2); }
+__host__ __device__ constexpr int64_t ws_o_index(int d, int tile, int row, int chunk) { return (int64_t)tile * BLOCK_M * d + ((int64_t)chunk * BLOCK_M + row) * 4; }
+__host__ __device__ constexpr int64_t ws_ml_index(int d, int tile, int row) { return (int64_t)kTiles * BLOCK_M * d + (tile * BLOCK_M + row) * 2; }
+__host__ __device__ constexpr int64_t ws_bytes(int d) { return kWsFlagBytes + (int64_t)kMaxCtas * 2 * ws_slot_floats(d) * 4; }
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -193,12 +191,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int b_mn_major, int m
       "=r"(a[o + 14]), "=r"(a[o + 15]), "=r"(a[o + 16]), "=r"(a[o + 17]), "=r"(a[o + 18]), "=r"(a[o + 19]),               \
       "=r"(a[o + 20]), "=r"(a[o + 21]), "=r"(a[o + 22]), "=r"(a[o + 23]), "=r"(a[o + 24]), "=r"(a[o + 25]),               \
       "=r"(a[o + 26]), "=r"(a[o + 27]), "=r"(a[o + 28]), "=r"(a[o + 29]), "=r"(a[o + 30]), "=r"(a[o + 31])
-#define HG_W32(a, o)                                                                                                     \
+#define HG_W16(a, o)                                                                                                     \
   "r"(a[o + 0]), "r"(a[o + 1]), "r"(a[o + 2]), "r"(a[o + 3]), "r"(a[o + 4]), "r"(a[o + 5]), "r"(a[o + 6]), "r"(a[o + 7]), \
       "r"(a[o + 8]), "r"(a[o + 9]), "r"(a[o + 10]), "r"(a[o + 11]), "r"(a[o + 12]), "r"(a[o + 13]), "r"(a[o + 14]),       \
-      "r"(a[o + 15]), "r"(a[o + 16]), "r"(a[o + 17]), "r"(a[o + 18]), "r"(a[o + 19]), "r"(a[o + 20]), "r"(a[o + 21]),     \
-      "r"(a[o + 22]), "r"(a[o + 23]), "r"(a[o + 24]), "r"(a[o + 25]), "r"(a[o + 26]), "r"(a[o + 27]), "r"(a[o + 28]),     \
-      "r"(a[o + 29]), "r"(a[o + 30]), "r"(a[o + 31])
+      "r"(a[o + 15])
+#define HG_W32(a, o) HG_W16(a, o), HG_W16(a, o + 16)
 
 // 32 lanes x 32 consecutive 32-bit columns: thread t of the warp gets lane (warp%4)*32 + t.
 #define HG_TMEM_LD32(taddr, a, o)                                                                               \
@@ -215,6 +212,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int b_mn_major, int m
       "%28,%29,%30,%31};" ::HG_W32(a, o),                                                                       \
       "r"(taddr)                                                                                                \
       : "memory")
+#define HG_TMEM_ST16(taddr, a, o)                                                                          \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::HG_W16(a, o), \
+               "r"(taddr)                                                                                  \
+               : "memory")
 
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -251,49 +252,6 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-__device__ __forceinline__ uint64_t fadd2_rm(uint64_t a, uint64_t b) {  // round toward -inf
-  uint64_t d;
-  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-// 2^x for a pair of fp32 on the FMA / ALU pipes instead of the MUFU unit (Cody-Waite split + degree-3
-// minimax polynomial, max relative error 8.8e-5 -- below the rounding of the 16-bit P it feeds):
-//   r = RM(x + 1.5*2^23) keeps floor(x) in its low mantissa bits, f = x - floor(x) in [0, 1),
-//   2^x = p(f) * 2^floor(x): the integer part is added straight into the exponent field of p(f).
-// Inputs are clamped at -127 (2^x underflows there anyway; without it the exponent field would wrap).
-__device__ __forceinline__ void exp2_poly_x2(float x0, float x1, float& p0, float& p1) {
-  const uint64_t kMagic = pack_f2(12582912.f, 12582912.f);
-  const uint64_t kC3 = pack_f2(0.077119089663028717041015625f, 0.077119089663028717041015625f);
-  const uint64_t kC2 = pack_f2(0.227564394474029541015625f, 0.227564394474029541015625f);
-  const uint64_t kC1 = pack_f2(0.695146143436431884765625f, 0.695146143436431884765625f);
-  const uint64_t kOne = pack_f2(1.f, 1.f);
-  const uint64_t x = pack_f2(fmaxf(x0, -127.f), fmaxf(x1, -127.f));
-  const uint64_t r = fadd2_rm(x, kMagic);
-  const uint64_t f = fsub2(x, fsub2(r, kMagic));
-  uint64_t p = ffma2(kC3, f, kC2);
-  p = ffma2(p, f, kC1);
-  p = ffma2(p, f, kOne);
-  float r0, r1, q0, q1;
-  unpack_f2(r, r0, r1);
-  unpack_f2(p, q0, q1);
-  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));
-  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
-}
-
-#define HG_W16(a, o)                                                                                                     \
-  "r"(a[o + 0]), "r"(a[o + 1]), "r"(a[o + 2]), "r"(a[o + 3]), "r"(a[o + 4]), "r"(a[o + 5]), "r"(a[o + 6]), "r"(a[o + 7]), \
-      "r"(a[o + 8]), "r"(a[o + 9]), "r"(a[o + 10]), "r"(a[o + 11]), "r"(a[o + 12]), "r"(a[o + 13]), "r"(a[o + 14]),       \
-      "r"(a[o + 15])
-#define HG_TMEM_ST16(taddr, a, o)                                                                          \
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::HG_W16(a, o), \
-               "r"(taddr)                                                                                  \
-               : "memory")
 
 // smem tile (generic-proxy writes fenced by the caller) -> global through the tensor map
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
@@ -301,23 +259,60 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void bulk_commit_and_wait() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 template <int ID, int THREADS>
 __device__ __forceinline__ void named_bar_sync() {
   asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(THREADS) : "memory");
 }
-__device__ __forceinline__ void named_bar_sync_rt(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// partials written by other SMs during this launch: read them at L2
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ld_cg_f2(const float* p) {
+  float2 r;
+  asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+
+#if defined(HG_PREFIX_TRACE) && !defined(HG_PREFIX_TU_CAUSAL)
+// Development aid (never in the shipped library): %globaltimer stamps [CTA][stage] of the most recent launch.
+// 0 entry | 1 set-up done | 2 griddepcontrol.wait passed | 3-5 first piece: first scores there, main loop done, epilogue
+// done | 6-8 the same for the last piece | 9 merge duties done | 10 CTA done   (3-9: row 0 of tile A's softmax warpgroup)
+__device__ long long g_prefix_trace[kMaxCtas * 16];
+__device__ __forceinline__ void ptrace(int stage) {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  g_prefix_trace[blockIdx.x * 16 + stage] = t;
+}
+#define HG_PTRACE(cond, stage) \
+  do {                         \
+    if (cond) ptrace(stage);   \
+  } while (0)
+#else
+#define HG_PTRACE(cond, stage) \
+  do {                         \
+  } while (0)
+#endif
 
 constexpr int kStages = 4;  // K/V ring depth
 
-// Ring slot u (u = -2 .. n_blocks-1) holds what MMA iteration u consumes: V_u (for P V of block u)
-// and K_{u+2} (for Q K^T of block u+2, issued in the same iteration); slots -2 and -1 carry only
-// K_0 / K_1 for the prologue.  One full and one empty barrier per slot.
+// Ring slot of MMA iteration u (u = -2 .. n-1 inside a piece of n key blocks) holds what that iteration consumes:
+// V_u (for P V of block u) and K_{u+2} (for Q K^T of block u+2, issued in the same iteration); iterations -2 and -1
+// carry only K_0 / K_1 for the prologue.  One full and one empty barrier per slot; slots and phases are counted
+// across pieces.
 template <int D>
 struct SmemLayout {
   static constexpr int kHalves = D / 64;                    // 64-element (128-byte) swizzle atoms along d
@@ -329,51 +324,173 @@ struct SmemLayout {
   static constexpr int kQ = 0;                              // 2 tiles (A, B)
   static constexpr int kKV = kQTileBytes * kTiles;
   static constexpr int kBars = kKV + kStageBytes * kStages;
-  static constexpr int kXchg = kBars + 512;  // split-column softmax: fp32 [parity][tile][half][row] row-max / row-sum exchange
-  static constexpr int kTotal = kXchg + 2 * kTiles * 2 * BLOCK_M * 4;
+  static constexpr int kTotal = kBars + 512;
 };
 
 struct Barriers {
-  uint64_t q_full[kTiles];
+  uint64_t q_full[kTiles], q_empty[kTiles];       // Q_t landed / Q_t smem (also the output staging tile) free again
   uint64_t kv_full[kStages], kv_empty[kStages];
   uint64_t s_full[kTiles][2], p_full[kTiles][2];  // per S buffer
   uint64_t pv_done[kTiles];                       // one phase per PV_t(j) (lazy-rescale path only)
-  uint64_t o_full[kTiles];                        // O_t complete
+  uint64_t o_full[kTiles], o_empty[kTiles];       // O_t of a piece complete / drained by the epilogue
   uint32_t tmem_base;
   uint32_t pad_;
-  uint64_t m_ready[kTiles][4][2];  // alternate-block softmax only: reference max of a block published (per lane quarter, block parity)
 };
+
+struct LevelDev {
+  void* out;           // [n_q_rows, hq, D]
+  float* lse;          // [n_q_rows, hq] or nullptr
+  const int32_t* cu;   // cu_seqlens_k (device) or nullptr
+  int k_len;           // uniform key count per group (cu == nullptr)
+  int pad_;
+};
+
+struct alignas(64) PrefixKernelParams {
+  CUtensorMap tmap_q;
+  CUtensorMap tmap_k[kMaxLevels], tmap_v[kMaxLevels], tmap_o[kMaxLevels];
+  SchedParams sched;
+  LevelDev lv[kMaxLevels];
+  int hkv;
+  float scale_log2;
+  uint32_t* ws_flags;  // workspace: epoch / exit counter / piece flags (nullptr: no unit is ever split)
+  float* ws_part;      // workspace: partial-result slots
+};
+
+// Everything a role needs to know about one piece (uniform over the CTA, recomputed by every role).
+struct Piece {
+  int level, head, kvh, mt;
+  int q_row0;      // first query row of the unit (tile A)
+  int rows_left;   // query rows from q_row0 to the end of the group (> 0)
+  int k_row0;      // first key row of the group in the level's K / V tensors
+  int k_len;       // keys of the group this unit may see (causal: up to the horizon of its last row)
+  int nb_group;    // key blocks covering k_len
+  int b_lo, n;     // first key block and number of key blocks of this piece (n may be 0)
+  int causal_off;
+  int split, slot, unit;
+};
+
+template <bool kCausal>
+__device__ __forceinline__ void resolve_piece(const PrefixKernelParams& P, const SchedPiece& sp, Piece& pc) {
+  const SchedLevel& L = P.sched.lv[sp.level];
+  const LevelDev& V = P.lv[sp.level];
+  pc.level = sp.level;
+  pc.head = sp.head;
+  pc.kvh = sp.head / (P.sched.hq / P.hkv);
+  pc.mt = sp.mt;
+  pc.q_row0 = sp.grp * L.q_per_group + sp.mt * (kTiles * BLOCK_M);
+  pc.rows_left = L.q_per_group - sp.mt * (kTiles * BLOCK_M);
+  if (V.cu != nullptr) {
+    pc.k_row0 = __ldg(V.cu + sp.grp);
+    pc.k_len = __ldg(V.cu + sp.grp + 1) - pc.k_row0;
+  } else {
+    pc.k_row0 = sp.grp * V.k_len;
+    pc.k_len = V.k_len;
+  }
+  pc.causal_off = 0;
+  if (kCausal) {
+    // bottom-right aligned (flash-attn >= 2.1): row r of the group sees keys j <= r + causal_off.  The unit streams
+    // only the keys its last row can see; the rows above it are masked per element in the diagonal blocks.
+    pc.causal_off = pc.k_len - L.q_per_group;  // >= 0 (checked by the launcher)
+    const int last_row = min(L.q_per_group, (sp.mt + 1) * (kTiles * BLOCK_M)) - 1;
+    pc.k_len = min(pc.k_len, last_row + pc.causal_off + 1);
+  }
+  pc.nb_group = (pc.k_len + BLOCK_N - 1) / BLOCK_N;
+  pc.b_lo = sp.b_lo;
+  pc.n = max(0, min(sp.b_hi, pc.nb_group) - sp.b_lo);
+  pc.split = sp.split;
+  pc.slot = sp.slot;
+  pc.unit = sp.unit;
+}
+
+// ---- cold paths of a split unit, kept out of line so that their registers do not weigh on the main loop -----------
+
+// Which CTAs hold the pieces of `unit` (key order) and in which workspace slot; returns the piece count.
+__device__ __noinline__ int unit_pieces(const SchedParams& S, int unit, int near, int* ctas, int* slots) {
+  const int k = sched_unit_pieces(S, unit, near, ctas, slots);
+  return k < kMaxUnitPieces ? k : kMaxUnitPieces;
+}
+
+// Role of this CTA's piece of a split unit: 0 = write the partial to the workspace (unit has 2 pieces, the other
+// CTA owns it), 1 = owner of a 2-piece unit (other = the slot index (cta * 2 + slot) of the tail piece's partial),
+// 2 = write the partial AND take part in the merge afterwards (3+ pieces).
+__device__ __noinline__ int split_role(const SchedParams& S, int unit, int cta, int* other) {
+  int ctas[kMaxUnitPieces], slots[kMaxUnitPieces];
+  const int k = unit_pieces(S, unit, cta, ctas, slots);
+  if (k > 2) return 2;
+  if (k == 2 && ctas[0] == cta) {
+    *other = ctas[1] * 2 + slots[1];
+    return 1;
+  }
+  return 0;
+}
+
+// Merge of a unit cut into 3+ pieces: this CTA's slice of the rows, one thread per row, 32 columns at a time.
+template <typename T, int D>
+__device__ __noinline__ void merge_duty(const SchedParams& S, const float* ws_part, const uint32_t* ws_flags, uint32_t epoch, int unit, int tid,
+                                        int lane, T* out, float* lse, int q_row0, int rows, int head, int hq) {
+  int ctas[kMaxUnitPieces], slots[kMaxUnitPieces];
+  const int k = unit_pieces(S, unit, blockIdx.x, ctas, slots);
+  int me = 0;
+  for (int p = 0; p < k; ++p)
+    if (ctas[p] == (int)blockIdx.x) me = p;
+  const int r_lo = (int)((long long)me * rows / k), r_hi = (int)((long long)(me + 1) * rows / k);
+  const int ntile = rows > BLOCK_M ? 2 : 1;
+  for (int i = lane; i < k * ntile; i += 32) {
+    const uint32_t* f = ws_flags + kWsWordFlags + (ctas[i / ntile] * 2 + slots[i / ntile]) * 2 + (i % ntile);
+    while ((int32_t)(ld_acquire_gpu(f) - epoch) < 0) {
+    }
+  }
+  __syncwarp();
+  for (int r = r_lo + tid; r < r_hi; r += kTiles * BLOCK_M) {
+    const int tt = r / BLOCK_M, rr = r % BLOCK_M;
+    float mx = -INFINITY, lsum = 0.f;
+    for (int p = 0; p < k; ++p) {
+      const float2 ml = ld_cg_f2(ws_part + (int64_t)(ctas[p] * 2 + slots[p]) * ws_slot_floats(D) + ws_ml_index(D, tt, rr));
+      if (ml.y > 0.f) mx = fmaxf(mx, ml.x);
+    }
+    for (int p = 0; p < k; ++p) {
+      const float2 ml = ld_cg_f2(ws_part + (int64_t)(ctas[p] * 2 + slots[p]) * ws_slot_floats(D) + ws_ml_index(D, tt, rr));
+      if (ml.y > 0.f) lsum += fast_exp2(ml.x - mx) * ml.y;
+    }
+    const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+    T* orow = out + ((int64_t)(q_row0 + r) * hq + head) * D;
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      float acc[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+      for (int p = 0; p < k; ++p) {
+        const float* slot = ws_part + (int64_t)(ctas[p] * 2 + slots[p]) * ws_slot_floats(D);
+        const float2 ml = ld_cg_f2(slot + ws_ml_index(D, tt, rr));
+        if (ml.y > 0.f) {
+          const float w = fast_exp2(ml.x - mx) * inv;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 o = ld_cg_f4(slot + ws_o_index(D, tt, rr, (c0 >> 2) + c));
+            acc[4 * c + 0] += w * o.x;
+            acc[4 * c + 1] += w * o.y;
+            acc[4 * c + 2] += w * o.z;
+            acc[4 * c + 3] += w * o.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; c += 8) {
+        uint4 w;
+        w.x = pack2<T>(acc[c + 0], acc[c + 1]);
+        w.y = pack2<T>(acc[c + 2], acc[c + 3]);
+        w.z = pack2<T>(acc[c + 4], acc[c + 5]);
+        w.w = pack2<T>(acc[c + 6], acc[c + 7]);
+        st_v4(orow + c0 + c, w);
+      }
+    }
+    if (lse != nullptr) lse[(int64_t)(q_row0 + r) * hq + head] = lsum > 0.f ? (mx + fast_log2(lsum)) * kLn2 : -INFINITY;
+  }
+}
 
 }  // namespace
 
-#if defined(HG_PREFIX_TRACE) && !defined(HG_PREFIX_TU_CAUSAL) && !defined(HG_PREFIX_TU_SPLIT) && !defined(HG_PREFIX_TU_SIMPLE) && !defined(HG_PREFIX_TU_ALT)
-// Development aid (never compiled into the shipped library): clock64 stamps of CTA (0,0).
-// Layout: [role][block j][slot]; role 0 = MMA thread, 1 = softmax warp of tile A, 2 = tile B.
-__device__ long long g_trace[3 * 64 * 8];
-#define HG_TRACE(role, j, slot)                                                                              \
-  do {                                                                                                       \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && (j) < 64) g_trace[((role) * 64 + (j)) * 8 + (slot)] = clock64(); \
-  } while (0)
-#else
-#define HG_TRACE(role, j, slot) \
-  do {                          \
-  } while (0)
-#endif
-
-// kCausal: bottom-right aligned causal mask inside every group (the prefill form, flash_attention(causal=True) of
-// hydragen/flash.py:284-306); a separate instantiation so that the decode-path kernel is exactly the unmasked code.
-//
-// kSplit: softmax organisation.  0 = one warpgroup per tile (thread = one row x 64 keys of a block, software
-// pipelined).  1 = TWO warpgroups per tile, each thread one row x 32 keys: four softmax warps per SM sub-partition
-// instead of two hide each other's TMEM / MUFU / barrier latencies (r01e: the two-warp form keeps the MUFU unit
-// only ~55 % busy); the two half-row maxima meet through shared memory and a 64-thread named barrier per block.
-template <typename T, int D, bool kCausal, int kSplit>
-__global__ void __launch_bounds__((kSplit == 1 || kSplit == 3) ? kThreadsSplit : kThreads, 1)
-    prefix_attn_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                             const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
-                             T* __restrict__ out, float* __restrict__ lse, const int32_t* __restrict__ cu_seqlens_k,
-                             int q_per_group, int tiles_per_group, int k_len_uniform, int hq, int hkv, float scale_log2,
-                             int kv_splits, int n_q_rows, int b_delay) {
+template <typename T, int D, bool kCausal>
+__global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __grid_constant__ PrefixKernelParams P) {
   using L = SmemLayout<D>;
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t kIdescQK = make_idesc(kFmt, 0, BLOCK_M, BLOCK_N);
@@ -384,79 +501,35 @@ __global__ void __launch_bounds__((kSplit == 1 || kSplit == 3) ? kThreadsSplit :
   Barriers* bars = reinterpret_cast<Barriers*>(smem + L::kBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // blockIdx.x = (group, m-tile, kv split): the splits of one tile sit next to each other
-  const int split = blockIdx.x % kv_splits;
-  const int tile = blockIdx.x / kv_splits, head = blockIdx.y;
-  const int grp = tile / tiles_per_group;
-  // causal: later row tiles see more keys -- launch them first
-  const int mt = kCausal ? tiles_per_group - 1 - tile % tiles_per_group : tile % tiles_per_group;
-  const int kvh = head / (hq / hkv);
-  const int q_row0 = grp * q_per_group + mt * (kTiles * BLOCK_M);
-  const int rows_left = q_per_group - mt * (kTiles * BLOCK_M);  // > 0
-  const bool two = rows_left > BLOCK_M;                         // tile B holds valid rows
-  int k_start, k_len;
-  if (cu_seqlens_k != nullptr) {
-    k_start = __ldg(cu_seqlens_k + grp);
-    k_len = __ldg(cu_seqlens_k + grp + 1) - k_start;
-  } else {
-    k_start = grp * k_len_uniform;
-    k_len = k_len_uniform;
-  }
-  if (kv_splits > 1) {
-    // split-KV: this CTA owns key blocks [split * bps, (split + 1) * bps) of its group and writes partial
-    // result number `split` (rows [split * n_q_rows, ...) of out / lse); the merge is the caller's combine.
-    const int bps = ((k_len + BLOCK_N - 1) / BLOCK_N + kv_splits - 1) / kv_splits;
-    const int first = split * bps * BLOCK_N;
-    k_start += first;
-    k_len = max(0, min(k_len - first, bps * BLOCK_N));
-    out += (int64_t)split * n_q_rows * hq * D;
-    if (lse != nullptr) lse += (int64_t)split * n_q_rows * hq;
-  }
-  // causal (bottom-right aligned, flash-attn >= 2.1): row r of the group sees keys j <= r + causal_off.  The CTA
-  // streams only the keys its last row can see; the rows above it are masked per element in the diagonal blocks.
-  int causal_off = 0;
-  if (kCausal) {
-    causal_off = k_len - q_per_group;  // >= 0 (checked by the launcher)
-    const int last_row = min(q_per_group, (mt + 1) * (kTiles * BLOCK_M)) - 1;
-    k_len = min(k_len, last_row + causal_off + 1);
-  }
-  const int n_blocks = (k_len + BLOCK_N - 1) / BLOCK_N;
-
-  if (n_blocks == 0) {  // empty prefix: out = 0, lse = -inf (uniform branch for the whole CTA)
-    const int rows = min(kTiles * BLOCK_M, rows_left);
-    for (int idx = threadIdx.x; idx < rows * (D / 8); idx += blockDim.x) {
-      const int r = idx / (D / 8), c = idx % (D / 8);
-      st_v4(out + ((int64_t)(q_row0 + r) * hq + head) * D + c * 8, make_uint4(0, 0, 0, 0));
-    }
-    if (lse != nullptr)
-      for (int r = threadIdx.x; r < rows; r += blockDim.x) lse[(int64_t)(q_row0 + r) * hq + head] = -INFINITY;
-    return;
-  }
+  const SchedParams& S = P.sched;
+  const int hq = S.hq;
+  const float scale_log2 = P.scale_log2;
+  HG_PTRACE(threadIdx.x == 0, 0);
 
   // ---- one-time setup --------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_v) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_q) : "memory");
+    for (int l = 0; l < S.n_levels; ++l) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_k[l]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_v[l]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_o[l]) : "memory");
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kTiles; ++i) {
       mbar_init(&bars->q_full[i], 1);
+      mbar_init(&bars->q_empty[i], 1);
       mbar_init(&bars->pv_done[i], 1);
       mbar_init(&bars->o_full[i], 1);
-      if constexpr (kSplit == 3) {
-        for (int q = 0; q < 4; ++q)
-          for (int b = 0; b < 2; ++b) mbar_init(&bars->m_ready[i][q][b], 32);
-      }
+      mbar_init(&bars->o_empty[i], BLOCK_M);
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bars->s_full[i][b], 1);
-        mbar_init(&bars->p_full[i][b], BLOCK_M * (kSplit == 1 ? 2 : 1));
+        mbar_init(&bars->p_full[i][b], BLOCK_M);
       }
     }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&bars->kv_full[i], 1);
-      mbar_init(&bars->kv_empty[i], two ? 2 : 1);  // one tcgen05.commit per MMA warp
+      mbar_init(&bars->kv_empty[i], kTiles);  // one arrival per MMA warp (a tcgen05.commit, or a plain arrive when its tile is idle)
     }
     fence_barrier_init();
   }
@@ -470,62 +543,82 @@ __global__ void __launch_bounds__((kSplit == 1 || kSplit == 3) ? kThreadsSplit :
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_base);
-  // The launch that follows on the stream (the fused append / suffix / combine kernel) is a programmatic
-  // dependent: let it start on SMs this grid leaves idle; it waits for this grid's completion itself
-  // before it reads the partial results written here.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  // This launch is itself a programmatic dependent of whatever precedes it on the stream (the previous
-  // layer's decode kernel, or the projection that produced q): everything above -- barrier init, TMEM
-  // allocation, descriptor prefetch -- overlapped its tail; q is read and out / lse are written only
-  // from here on.  (No-op when launched without the attribute.)
+  HG_PTRACE(threadIdx.x == 0, 1);
+  // This launch may be a programmatic dependent of whatever precedes it on the stream (the previous layer's decode
+  // kernel, or the projection that produced q): everything above overlapped its tail; q and the workspace are read,
+  // and out / lse written, only from here on.  Only then is the launch that follows (the fused append / suffix /
+  // combine kernel) allowed to start: its own early work (KV append, suffix walk) then never overtakes the kernel in
+  // front of this one, and it waits for this grid's completion itself before it reads the results written here.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  HG_PTRACE(threadIdx.x == 0, 2);
 
-  // Register budget (setmaxnreg must sit inside the role branch it applies to): the producer
-  // warpgroup gives registers back, the two softmax warpgroups (128 live fp32 scores per thread)
-  // take them: 128 x 56 + 256 x 224 = 384 x 168, the launch-time allocation (r01h: with 88 / 208 the running max, row
-  // sum and loop state of the softmax threads were spilled to local memory, on the serial path between two blocks).
-  // (split-column form: 640 threads x 96 at launch -> 128 x 64 + 512 x 104.)
+  // Register budget (setmaxnreg must sit inside the role branch it applies to): the producer warpgroup gives registers
+  // back, the two softmax warpgroups (128 live fp32 scores per thread) take them: 128 x 56 + 256 x 224 = 384 x 168,
+  // the launch-time allocation.
   if (warp < 4) {
-    if constexpr (kSplit == 1 || kSplit == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if (warp == 0) {
-    // =============================== TMA producer ===========================================
-    if (elect_one()) {
-      for (int t = 0; t < (two ? 2 : 1); ++t) {
-        mbar_expect_tx(&bars->q_full[t], L::kQTileBytes);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // =============================== TMA producer ===========================================
+      const bool leader = elect_one();
+      uint32_t ri = 0;              // ring iterations issued (all pieces)
+      uint32_t nq[kTiles] = {0, 0};  // Q loads issued per tile
+      SchedIter it;
+      SchedPiece sp;
+      sched_begin(S, blockIdx.x, it);
+      while (sched_next(S, it, sp)) {
+        Piece pc;
+        resolve_piece<kCausal>(P, sp, pc);
+        if (pc.n == 0) continue;
+        const int n = pc.n;
+        const int key0 = pc.k_row0 + pc.b_lo * BLOCK_N;
+        const int ntile = pc.rows_left > BLOCK_M ? 2 : 1;
+        const CUtensorMap* tk = &P.tmap_k[pc.level];
+        const CUtensorMap* tv = &P.tmap_v[pc.level];
+        for (int u = -2; u < n; ++u) {
+          if (u == 0) {
+            // Q after the two prologue K blocks: its smem is the previous piece's output staging tile
+            for (int t = 0; t < ntile; ++t) {
+              mbar_wait(&bars->q_empty[t], (nq[t] & 1) ^ 1);
+              if (leader) {
+                mbar_expect_tx(&bars->q_full[t], L::kQTileBytes);
 #pragma unroll
-        for (int h = 0; h < L::kHalves; ++h)
-          tma_load_2d(smem + L::kQ + t * L::kQTileBytes + h * L::kQHalfBytes, &tmap_q, head * D + h * 64, q_row0 + t * BLOCK_M,
-                      &bars->q_full[t]);
-      }
-      for (int u = -2; u < n_blocks; ++u) {
-        const int st = (u + 2) % kStages;
-        const bool has_v = u >= 0, has_k = u + 2 < n_blocks;
-        if (!has_v && !has_k) continue;
-        uint8_t* base = smem + L::kKV + st * L::kStageBytes;
-        mbar_wait(&bars->kv_empty[st], (((u + 2) / kStages) & 1) ^ 1);
-        mbar_expect_tx(&bars->kv_full[st], (has_v ? L::kKVTileBytes : 0) + (has_k ? L::kKVTileBytes : 0));
-        if (has_k) {
+                for (int h = 0; h < L::kHalves; ++h)
+                  tma_load_2d(smem + L::kQ + t * L::kQTileBytes + h * L::kQHalfBytes, &P.tmap_q, pc.head * D + h * 64,
+                              pc.q_row0 + t * BLOCK_M, &bars->q_full[t]);
+              }
+              ++nq[t];
+            }
+          }
+          const bool has_v = u >= 0, has_k = u + 2 < n;
+          if (!has_v && !has_k) continue;
+          const int st = ri % kStages;
+          uint8_t* base = smem + L::kKV + st * L::kStageBytes;
+          mbar_wait(&bars->kv_empty[st], ((ri / kStages) & 1) ^ 1);
+          if (leader) {
+            mbar_expect_tx(&bars->kv_full[st], (has_v ? L::kKVTileBytes : 0) + (has_k ? L::kKVTileBytes : 0));
+            if (has_k) {
 #pragma unroll
-          for (int h = 0; h < L::kHalves; ++h)
-            tma_load_2d(base + L::kKVTileBytes + h * L::kKVHalfBytes, &tmap_k, kvh * D + h * 64, k_start + (u + 2) * BLOCK_N,
-                        &bars->kv_full[st]);
+              for (int h = 0; h < L::kHalves; ++h)
+                tma_load_2d(base + L::kKVTileBytes + h * L::kKVHalfBytes, tk, pc.kvh * D + h * 64, key0 + (u + 2) * BLOCK_N,
+                            &bars->kv_full[st]);
+            }
+            if (has_v) {
+#pragma unroll
+              for (int h = 0; h < L::kHalves; ++h)
+                tma_load_2d(base + h * L::kKVHalfBytes, tv, pc.kvh * D + h * 64, key0 + u * BLOCK_N, &bars->kv_full[st]);
+            }
+          }
+          ++ri;
         }
-        if (has_v) {
-#pragma unroll
-          for (int h = 0; h < L::kHalves; ++h)
-            tma_load_2d(base + h * L::kKVHalfBytes, &tmap_v, kvh * D + h * 64, k_start + u * BLOCK_N, &bars->kv_full[st]);
-        }
       }
-    }
-  } else if (warp == 1 || warp == 3) {
-    // =============================== MMA issuers (warp 1: tile A, warp 3: tile B) ==============
-    // The whole warp walks the loop and the barriers (warp-uniform, so descriptors stay in uniform
-    // registers); one elected lane issues tcgen05.mma / tcgen05.commit.  Per block j and tile t:
-    //   P V of block j, then Q K^T of block j+2 into the S buffer P_t(j) just vacated (same thread,
-    //   same issue order: no barrier needed between them).
-    const int t = warp >> 1;
-    if (t == 0 || two) {
+    } else if (warp == 1 || warp == 3) {
+      // =============================== MMA issuers (warp 1: tile A, warp 3: tile B) ==============
+      // The whole warp walks the loop and the barriers (warp-uniform, so descriptors stay in uniform registers); one
+      // elected lane issues tcgen05.mma / tcgen05.commit.  Per block j and tile t: P V of block j, then Q K^T of
+      // block j+2 into the S buffer P_t(j) just vacated (same thread, same issue order: no barrier between them).
+      // A warp whose tile holds no rows in a piece still walks the ring and releases its slots.
+      const int t = warp >> 1;
       const bool leader = elect_one();
       constexpr uint32_t kHiK = desc_hi(1024);  // SWIZZLE_128B: 8-row groups 1024 B apart
       const uint32_t q_lo = desc_lo(smem_u32(smem + L::kQ + t * L::kQTileBytes), 0);
@@ -555,462 +648,148 @@ __global__ void __launch_bounds__((kSplit == 1 || kSplit == 3) ? kThreadsSplit :
           umma_ts(o_tmem, p_tmem + kk * 8, v_lo + kk * (2048 >> 4), kHiK, kIdescPV, (first && kk == 0) ? 0u : 1u);
       };
 
-      // prologue: S_t(0), S_t(1) -- the softmax warpgroup then always finds its next block ready
-      mbar_wait(&bars->q_full[t], 0);
-      for (int u = -2; u < 0; ++u) {
-        if (u + 2 < n_blocks) {
-          const int st = (u + 2) % kStages;
-          mbar_wait(&bars->kv_full[st], 0);
-          tc_fence_after();
-          if (leader) {
-            issue_qk(st, (u + 2) & 1);
-            umma_commit(&bars->s_full[t][(u + 2) & 1]);
-            umma_commit(&bars->kv_empty[st]);
+      uint32_t ri = 0;  // ring iterations consumed (all pieces, mirrors the producer)
+      uint32_t g = 0;   // key blocks of tile t issued so far: S buffer = g & 1, phases count in g
+      uint32_t np = 0;  // pieces in which tile t was active
+      SchedIter it;
+      SchedPiece sp;
+      sched_begin(S, blockIdx.x, it);
+      while (sched_next(S, it, sp)) {
+        Piece pc;
+        resolve_piece<kCausal>(P, sp, pc);
+        if (pc.n == 0) continue;
+        const int n = pc.n;
+        const bool active = t == 0 || pc.rows_left > BLOCK_M;
+        // prologue: S_t(0), S_t(1) -- the softmax warpgroup then always finds its next block ready
+        for (int u = -2; u < 0; ++u) {
+          if (u + 2 < n) {
+            const int st = ri % kStages;
+            mbar_wait(&bars->kv_full[st], (ri / kStages) & 1);
+            if (active) {
+              if (u == -2) mbar_wait(&bars->q_full[t], np & 1);
+              tc_fence_after();
+              if (leader) {
+                const int sb = (g + u + 2) & 1;
+                issue_qk(st, sb);
+                umma_commit(&bars->s_full[t][sb]);
+                umma_commit(&bars->kv_empty[st]);
+              }
+            } else if (leader) {
+              mbar_arrive(&bars->kv_empty[st]);
+            }
+            __syncwarp();
+            ++ri;
+          }
+        }
+        // O_t of the previous piece must have been drained by its epilogue before P V overwrites it
+        if (active) mbar_wait(&bars->o_empty[t], (np & 1) ^ 1);
+        for (int j = 0; j < n; ++j) {
+          const int st = ri % kStages;
+          mbar_wait(&bars->kv_full[st], (ri / kStages) & 1);
+          if (active) {
+            const uint32_t gj = g + j;
+            const int b = gj & 1;
+            mbar_wait(&bars->p_full[t][b], (gj >> 1) & 1);
+            tc_fence_after();
+            if (leader) {
+              issue_pv(st, b, j == 0);
+              umma_commit(&bars->pv_done[t]);
+              if (j + 1 == n) umma_commit(&bars->o_full[t]);
+              if (j + 2 < n) {
+                issue_qk(st, b);
+                umma_commit(&bars->s_full[t][b]);
+              }
+              umma_commit(&bars->kv_empty[st]);
+            }
+          } else if (leader) {
+            mbar_arrive(&bars->kv_empty[st]);
           }
           __syncwarp();
+          ++ri;
+        }
+        if (active) {
+          g += n;
+          ++np;
         }
       }
-      for (int j = 0; j < n_blocks; ++j) {
-        const int b = j & 1;
-        const int st = (j + 2) % kStages;
-        const bool more = j + 2 < n_blocks;
-        if (t == 0) HG_TRACE(0, j, 0);
-        mbar_wait(&bars->kv_full[st], ((j + 2) / kStages) & 1);
-        if (t == 0) HG_TRACE(0, j, 1);
-        mbar_wait(&bars->p_full[t][b], (j >> 1) & 1);
-        if (t == 0) HG_TRACE(0, j, 2);
-        tc_fence_after();
-        if (leader) {
-          issue_pv(st, b, j == 0);
-          umma_commit(j + 1 < n_blocks ? &bars->pv_done[t] : &bars->o_full[t]);
-          if (more) {
-            issue_qk(st, b);
-            umma_commit(&bars->s_full[t][b]);
-          }
-          umma_commit(&bars->kv_empty[st]);
-        }
-        __syncwarp();
-        if (t == 0) HG_TRACE(0, j, 3);
-      }
-    }
-  }
-  } else if constexpr (kSplit == 1) {
-    // =============================== softmax, split-column form ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    const int sw = warp - 4;          // 0 .. 15
-    const int t = sw >> 3;            // tile owned by this pair of warpgroups
-    const int half = (sw >> 2) & 1;   // which 32 keys of every 64-key block (and which D/2 columns of O)
-    const int rows_valid = min(BLOCK_M, rows_left - t * BLOCK_M);
-    if (rows_valid > 0) {
-      constexpr int DH = D / 2;
-      const int wq = warp & 3;        // == sw % 4: the TMEM lane quarter this warp may access
-      const int row = wq * 32 + lane;
-      const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-      const uint32_t o_addr = tmem + lane_base + tmem_o(t) + (uint32_t)(half * DH);
-      float* xchg = reinterpret_cast<float*>(smem + L::kXchg);
-      const int pair_bar = 1 + t * 4 + wq;  // the two warps that own the same 32 rows (named barriers 1..8)
-      float m_used = -INFINITY, l = 0.f;
-      const int row_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + row + causal_off + 1 : 0x7fffffff;
-      const int tile_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + causal_off + 1 : 0x7fffffff;
-      const bool ragged = (k_len % BLOCK_N) != 0;
-      // value of the partner warp (same rows, other key half) for this thread's row; double buffered by parity
-      auto exchange = [&](int parity, float mine) {
-        float* slot = xchg + ((parity * kTiles + t) * 2) * BLOCK_M;
-        slot[half * BLOCK_M + row] = mine;
-        tc_fence_before();
-        named_bar_sync_rt(pair_bar, 64);
-        tc_fence_after();
-        return slot[(half ^ 1) * BLOCK_M + row];
-      };
-      for (int j = 0; j < n_blocks; ++j) {
-        const int b = j & 1;
-        const uint32_t s_addr = tmem + lane_base + tmem_s(t, b);
-        mbar_wait(&bars->s_full[t][b], (j >> 1) & 1);
-        tc_fence_after();
-        uint32_t sc[32];
-        HG_TMEM_LD32(s_addr + half * 32, sc, 0);
-        tmem_wait_ld();
-        if ((ragged && j + 1 == n_blocks) || (j + 1) * BLOCK_N > tile_end) {  // warp-uniform
-          const int rem = min(k_len, row_end) - j * BLOCK_N - half * 32;
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c >= rem) sc[c] = 0xff800000u;  // -inf
-        }
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(sc[c + 0]), __uint_as_float(sc[c + 1])));
-          mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(sc[c + 2]), __uint_as_float(sc[c + 3])));
-          mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(sc[c + 4]), __uint_as_float(sc[c + 5])));
-          mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(sc[c + 6]), __uint_as_float(sc[c + 7])));
-        }
-        const float m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        // Both warps of the pair hold their scores in registers once they pass the barrier inside exchange():
-        // only then may either of them overwrite the S buffer with its half of P.
-        const float m_blk = fmaxf(m_half, exchange(b, m_half));
-        const float m_new = fmaxf(m_used, m_blk);
-        if (j == 0) {
-          m_used = m_new;
-        } else {
-          const bool need = (m_new - m_used) * scale_log2 > kRescaleThreshold;
-          if (__any_sync(0xffffffffu, need)) {  // the partner warp sees the same rows and takes the same branch
-            mbar_wait(&bars->pv_done[t], (j - 1) & 1);
-            tc_fence_after();
-            const float alpha = need ? fast_exp2((m_used - m_new) * scale_log2) : 1.f;
-            if (need) {
-              m_used = m_new;
-              l *= alpha;
-            }
-#pragma unroll
-            for (int c0 = 0; c0 < DH; c0 += 32) {
-              uint32_t o[32];
-              HG_TMEM_LD32(o_addr + c0, o, 0);
-              tmem_wait_ld();
-#pragma unroll
-              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-              HG_TMEM_ST32(o_addr + c0, o, 0);
-            }
-          }
-        }
-        const float neg_mc = -m_used * scale_log2;
-        const uint64_t scale2 = pack_f2(scale_log2, scale_log2), neg2 = pack_f2(neg_mc, neg_mc);
-        uint64_t ps2[2] = {0ull, 0ull};
-        uint32_t pk[16];
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float x0, x1;
-          unpack_f2(ffma2(pack_f2(__uint_as_float(sc[c]), __uint_as_float(sc[c + 1])), scale2, neg2), x0, x1);
-          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-          ps2[(c >> 1) & 1] = fadd2(ps2[(c >> 1) & 1], pack_f2(p0, p1));
-          pk[c >> 1] = pack2<T>(p0, p1);
-        }
-        HG_TMEM_ST16(s_addr + half * 16, pk, 0);  // P_t(j): keys [half*32, half*32+32) -> columns [half*16, half*16+16)
-        {
-          float a0, a1;
-          unpack_f2(fadd2(ps2[0], ps2[1]), a0, a1);
-          l += a0 + a1;
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&bars->p_full[t][b]);
-      }
-
-      // ---- epilogue: this warp owns columns [half*DH, half*DH + DH) of its 32 rows of O_t ----
-      mbar_wait(&bars->o_full[t], 0);
-      tc_fence_after();
-      l += exchange(n_blocks & 1, l);  // row sum of both key halves
-      const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
-      const int tile_row0 = q_row0 + t * BLOCK_M;
-      if (rows_valid == BLOCK_M) {
-        uint8_t* stage = smem + L::kQ + t * L::kQTileBytes;
-#pragma unroll
-        for (int c0 = 0; c0 < DH; c0 += 32) {
-          uint32_t o[32];
-          HG_TMEM_LD32(o_addr + c0, o, 0);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            uint4 w;
-            w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
-            w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
-            w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
-            w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
-            const int chunk = (half * DH + c0 + c) >> 3;  // 16-byte chunk of the row
-            uint8_t* dst = stage + (chunk >> 3) * L::kQHalfBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = w;
-          }
-        }
-        fence_proxy_async();
-        named_bar_sync_rt(9 + t, 2 * BLOCK_M);  // the eight warps of this tile
-        if (half == 0 && wq == 0 && lane == 0) {
-#pragma unroll
-          for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&tmap_o, stage + h * L::kQHalfBytes, head * D + h * 64, split * n_q_rows + tile_row0);
-          bulk_commit_and_wait();
-        }
-      } else {
-        const bool row_ok = row < rows_valid;
-        T* orow = out + ((int64_t)(tile_row0 + row) * hq + head) * D + half * DH;
-#pragma unroll
-        for (int c0 = 0; c0 < DH; c0 += 32) {
-          uint32_t o[32];
-          HG_TMEM_LD32(o_addr + c0, o, 0);
-          tmem_wait_ld();
-          if (row_ok) {
-#pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-              uint4 w;
-              w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
-              w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
-              w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
-              w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
-              st_v4(orow + c0 + c, w);
-            }
-          }
-        }
-      }
-      if (half == 0 && row < rows_valid && lse != nullptr)
-        lse[(int64_t)(tile_row0 + row) * hq + head] = (l > 0.f) ? (m_used * scale_log2 + fast_log2(l)) * kLn2 : -INFINITY;
-      tc_fence_before();
-    }
-  } else if constexpr (kSplit == 3) {
-    // =============================== softmax, alternate-block form ============================
-    // Two warpgroups per tile; the warps that own the same 32 rows take the key blocks in turn (even / odd), each with
-    // its own S/P buffer (the double buffer IS the block parity), so four softmax warps share a sub-partition without
-    // a per-block exchange of scores.  What the two share per row is the lazily updated reference max: the warp of
-    // block j publishes the reference it used (shared memory + an mbarrier with 32 arrivals) as soon as it has the
-    // row max of its block -- long before it is done with the block -- and the warp of block j+1 picks it up.  Each
-    // warp keeps its own partial row sum relative to the reference it last saw; they meet once, in the epilogue.
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    const int sw = warp - 4;          // 0 .. 15
-    const int t = sw >> 3;            // tile owned by this pair of warpgroups
-    const int par = (sw >> 2) & 1;    // this warp takes key blocks j with j % 2 == par (and, in the epilogue, D/2 columns of O)
-    const int rows_valid = min(BLOCK_M, rows_left - t * BLOCK_M);
-    if (rows_valid > 0) {
-      constexpr int DH = D / 2;
-      const int half = par;
-      const int wq = warp & 3;        // == sw % 4: the TMEM lane quarter this warp may access
-      const int row = wq * 32 + lane;
-      const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-      const uint32_t o_all = tmem + lane_base + tmem_o(t);        // every column of this row of O_t (lazy rescale)
-      const uint32_t o_addr = o_all + (uint32_t)(half * DH);      // the columns this warp writes out
-      const uint32_t s_addr = tmem + lane_base + tmem_s(t, par);  // this warp's S / P buffer
-      float* xchg = reinterpret_cast<float*>(smem + L::kXchg);
-      volatile float* m_mine = xchg + ((par * kTiles + t) * 2 + 0) * BLOCK_M + row;          // reference published by this warp
-      volatile float* m_other = xchg + (((par ^ 1) * kTiles + t) * 2 + 0) * BLOCK_M + row;   // ... by its partner
-      volatile float* l_mine = xchg + ((par * kTiles + t) * 2 + 1) * BLOCK_M + row;
-      volatile float* l_other = xchg + (((par ^ 1) * kTiles + t) * 2 + 1) * BLOCK_M + row;
-      uint64_t* ready_mine = &bars->m_ready[t][wq][par];
-      uint64_t* ready_other = &bars->m_ready[t][wq][par ^ 1];
-      const int pair_bar = 1 + t * 4 + wq;  // the two warps that own the same 32 rows (named barriers 1..8)
-      float m_w = -INFINITY;  // reference this warp's partial row sum is expressed in
-      float l = 0.f;
-      const int row_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + row + causal_off + 1 : 0x7fffffff;
-      const int tile_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + causal_off + 1 : 0x7fffffff;
-      const bool ragged = (k_len % BLOCK_N) != 0;
-      for (int j = par; j < n_blocks; j += 2) {
-        mbar_wait(&bars->s_full[t][par], (j >> 1) & 1);
-        tc_fence_after();
-        const bool masked = (ragged && j + 1 == n_blocks) || (j + 1) * BLOCK_N > tile_end;  // warp-uniform
-        const int rem = min(k_len, row_end) - j * BLOCK_N;
-        uint32_t sc[32];
-        // ---- pass 1: row max of the block (the scores are fetched again in pass 2: TMEM reads are cheap, registers are not)
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          HG_TMEM_LD32(s_addr + h * 32, sc, 0);
-          tmem_wait_ld();
-          if (masked) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (h * 32 + c >= rem) sc[c] = 0xff800000u;  // -inf
-          }
-#pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(sc[c + 0]), __uint_as_float(sc[c + 1])));
-            mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(sc[c + 2]), __uint_as_float(sc[c + 3])));
-            mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(sc[c + 4]), __uint_as_float(sc[c + 5])));
-            mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(sc[c + 6]), __uint_as_float(sc[c + 7])));
-          }
-        }
-        const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        // ---- the reference this block is exponentiated against
-        float m_used;
-        if (j == 0) {
-          m_used = m_blk;
-        } else {
-          mbar_wait(ready_other, ((j - 1) >> 1) & 1);  // block j-1's warp has published its reference
-          const float m_prev = *m_other;
-          const float m_new = fmaxf(m_prev, m_blk);
-          const bool need = (m_new - m_prev) * scale_log2 > kRescaleThreshold;
-          m_used = m_prev;
-          if (__any_sync(0xffffffffu, need)) {
-            // rare: O_t must be complete up to P_t(j-1) V_{j-1} before it is rescaled in place; P_t(j) has not been
-            // released yet, and block j+1's warp cannot release P_t(j+1)'s rescale before P_t(j) V_j is done.
-            mbar_wait(&bars->pv_done[t], (j - 1) & 1);
-            tc_fence_after();
-            const float alpha = need ? fast_exp2((m_prev - m_new) * scale_log2) : 1.f;
-            if (need) m_used = m_new;
-#pragma unroll
-            for (int c0 = 0; c0 < D; c0 += 32) {
-              uint32_t o[32];
-              HG_TMEM_LD32(o_all + c0, o, 0);
-              tmem_wait_ld();
-#pragma unroll
-              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-              HG_TMEM_ST32(o_all + c0, o, 0);
-            }
-          }
-        }
-        *m_mine = m_used;
-        mbar_arrive(ready_mine);  // release: the store above is visible to whoever sees this phase complete
-        if (m_w != m_used) {      // bring this warp's partial row sum to the reference in force (first block: 0 * 0)
-          l *= fast_exp2((m_w - m_used) * scale_log2);
-          m_w = m_used;
-        }
-        // ---- pass 2: exponentials, row sum, P_t(j)
-        const float neg_mc = -m_used * scale_log2;
-        const uint64_t scale2 = pack_f2(scale_log2, scale_log2), neg2 = pack_f2(neg_mc, neg_mc);
-        uint64_t ps2[2] = {0ull, 0ull};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          HG_TMEM_LD32(s_addr + h * 32, sc, 0);
-          tmem_wait_ld();
-          if (masked) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (h * 32 + c >= rem) sc[c] = 0xff800000u;
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float x0, x1;
-            unpack_f2(ffma2(pack_f2(__uint_as_float(sc[c]), __uint_as_float(sc[c + 1])), scale2, neg2), x0, x1);
-            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-            ps2[(c >> 1) & 1] = fadd2(ps2[(c >> 1) & 1], pack_f2(p0, p1));
-            pk[c >> 1] = pack2<T>(p0, p1);
-          }
-          // keys [h*32, h*32+32) -> columns [h*16, h*16+16): only columns whose scores this thread has already consumed
-          HG_TMEM_ST16(s_addr + h * 16, pk, 0);
-        }
-        {
-          float a0, a1;
-          unpack_f2(fadd2(ps2[0], ps2[1]), a0, a1);
-          l += a0 + a1;
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&bars->p_full[t][par]);
-      }
-
-      // ---- common reference, row-sum exchange, epilogue on this warp's D/2 columns ------------
-      const int last = n_blocks - 1;
-      float m_final = m_w;
-      if ((last & 1) != par) {
-        mbar_wait(ready_other, (last >> 1) & 1);
-        m_final = *m_other;
-      }
-      if (m_w != m_final) l *= fast_exp2((m_w - m_final) * scale_log2);
-      mbar_wait(&bars->o_full[t], 0);
-      tc_fence_after();
-      *l_mine = l;
-      tc_fence_before();
-      named_bar_sync_rt(pair_bar, 64);
-      tc_fence_after();
-      l += *l_other;
-      const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
-      const int tile_row0 = q_row0 + t * BLOCK_M;
-      if (rows_valid == BLOCK_M) {
-        uint8_t* stage = smem + L::kQ + t * L::kQTileBytes;
-#pragma unroll
-        for (int c0 = 0; c0 < DH; c0 += 32) {
-          uint32_t o[32];
-          HG_TMEM_LD32(o_addr + c0, o, 0);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            uint4 w;
-            w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
-            w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
-            w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
-            w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
-            const int chunk = (half * DH + c0 + c) >> 3;  // 16-byte chunk of the row
-            uint8_t* dst = stage + (chunk >> 3) * L::kQHalfBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = w;
-          }
-        }
-        fence_proxy_async();
-        named_bar_sync_rt(9 + t, 2 * BLOCK_M);  // the eight warps of this tile
-        if (half == 0 && wq == 0 && lane == 0) {
-#pragma unroll
-          for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&tmap_o, stage + h * L::kQHalfBytes, head * D + h * 64, split * n_q_rows + tile_row0);
-          bulk_commit_and_wait();
-        }
-      } else {
-        const bool row_ok = row < rows_valid;
-        T* orow = out + ((int64_t)(tile_row0 + row) * hq + head) * D + half * DH;
-#pragma unroll
-        for (int c0 = 0; c0 < DH; c0 += 32) {
-          uint32_t o[32];
-          HG_TMEM_LD32(o_addr + c0, o, 0);
-          tmem_wait_ld();
-          if (row_ok) {
-#pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-              uint4 w;
-              w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
-              w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
-              w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
-              w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
-              st_v4(orow + c0 + c, w);
-            }
-          }
-        }
-      }
-      if (half == 0 && row < rows_valid && lse != nullptr)
-        lse[(int64_t)(tile_row0 + row) * hq + head] = (l > 0.f) ? (m_final * scale_log2 + fast_log2(l)) * kLn2 : -INFINITY;
-      tc_fence_before();
     }
   } else {
-    // =============================== softmax / correction / epilogue ==========================
+    // =============================== softmax warpgroups =====================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    const int t = (warp - 4) >> 2;     // tile owned by this warpgroup
-    const int rows_valid = min(BLOCK_M, rows_left - t * BLOCK_M);
-    if (rows_valid > 0) {
-      const int wq = warp & 3;           // == warp % 4: the TMEM lane quarter this warp may access
-      const int row = wq * 32 + lane;    // row of the tile == TMEM lane
-      const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-      const uint32_t o_addr = tmem + lane_base + tmem_o(t);
-      float m_used = -INFINITY;          // raw-score max the exponentials are referenced to
+    const int t = (warp - 4) >> 2;      // tile owned by this warpgroup
+    const int wq = warp & 3;            // == warp % 4: the TMEM lane quarter this warp may access
+    const int row = wq * 32 + lane;     // row of the tile == TMEM lane
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    const uint32_t o_addr = tmem + lane_base + tmem_o(t);
+    uint32_t* const ws_flags = P.ws_flags;
+    const uint32_t epoch = ws_flags != nullptr ? *reinterpret_cast<volatile uint32_t*>(ws_flags + kWsWordEpoch) + 1u : 0u;
+    uint32_t g = 0, np = 0;  // as in the MMA warp of this tile
+    int duty_unit[2] = {-1, -1};  // units cut into more than two pieces that this CTA holds a piece of (by workspace slot)
+    bool first_piece = true;
+    SchedIter it;
+    SchedPiece sp;
+    sched_begin(S, blockIdx.x, it);
+    while (sched_next(S, it, sp)) {
+      Piece pc;
+      resolve_piece<kCausal>(P, sp, pc);
+      const int rows_valid = min(BLOCK_M, pc.rows_left - t * BLOCK_M);
+      if (rows_valid <= 0) {  // tile B of a unit with at most 128 rows: nothing to compute, but the merge duty is shared
+        if (pc.split) {
+          int other;
+          if (split_role(S, pc.unit, blockIdx.x, &other) == 2) duty_unit[pc.slot] = pc.unit;
+        }
+        continue;
+      }
+      const int n = pc.n;
+      const int k_len = pc.k_len;
+      float m_used = -INFINITY;  // raw-score max the exponentials are referenced to
       float l = 0.f;
 
-      // Software pipeline over key blocks.  Per block the warp issues 64 MUFU exp2; everything else it
-      // has to do -- the scale FFMAs, the row sums and the 16-bit packing of block j, and (once S_t(j+1)
-      // can have landed: its Q K^T is only issued after P_t(j-1) was consumed) fetching the scores of
-      // block j+1 from TMEM and reducing them to their row max -- is written interleaved with those MUFU
-      // requests in groups of 8, so that the in-order warp always has independent work behind them and
-      // the two softmax warps sharing an SM sub-partition do not convoy on the MUFU unit.  Two score
-      // register arrays alternate between "being exponentiated" and "being fetched".
-      // first key (group-relative) this thread's row may NOT see; tile_lim: the same for the tile's first row
-      const int row_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + row + causal_off + 1 : 0x7fffffff;
-      const int tile_end = kCausal ? mt * (kTiles * BLOCK_M) + t * BLOCK_M + causal_off + 1 : 0x7fffffff;
-      const bool ragged = (k_len % BLOCK_N) != 0;
-      // block jb holds a key some row of this tile must not see (warp-uniform)
-      auto needs_mask = [&](int jb) { return (ragged && jb + 1 == n_blocks) || (jb + 1) * BLOCK_N > tile_end; };
-      if constexpr (kSplit == 2) {
-        // "simple" form (experimental, HYDRAGEN_B200_PREFIX_SOFTMAX=simple): no software pipelining -- per block:
-        // wait for S_t(j), fetch it, row max, (lazy rescale), exp / sum / pack, store P_t(j), arrive.  The isolated
-        // instruction stream in this shape needs 1279 cycles per block pair with two warps per sub-partition
-        // (scripts/microbench/softmax_stream.cu, r01r) against the 1625 of the pipelined loop inside the kernel.
-        for (int j = 0; j < n_blocks; ++j) {
-          const int b = j & 1;
-          const uint32_t s_addr = tmem + lane_base + tmem_s(t, b);
-          mbar_wait(&bars->s_full[t][b], (j >> 1) & 1);
-          tc_fence_after();
-          uint32_t sc[BLOCK_N];
-          HG_TMEM_LD32(s_addr + 0, sc, 0);
-          HG_TMEM_LD32(s_addr + 32, sc, 32);
-          tmem_wait_ld();
-          if (needs_mask(j)) {
-            const int rem = min(k_len, row_end) - j * BLOCK_N;
+      if (n > 0) {
+        // Software pipeline over key blocks.  Per block the warp issues 64 MUFU exp2; everything else it has to do --
+        // the scale FFMAs, the row sums and the 16-bit packing of block j, and (once S_t(j+1) can have landed: its
+        // Q K^T is only issued after P_t(j-1) was consumed) fetching the scores of block j+1 from TMEM and reducing
+        // them to their row max -- is written interleaved with those MUFU requests in groups of 8, so that the
+        // in-order warp always has independent work behind them.  Two score register arrays alternate between
+        // "being exponentiated" and "being fetched".
+        // row_end: first key (group-relative) this thread's row may NOT see; tile_end: the same for the tile's first row
+        const int row_end = kCausal ? pc.mt * (kTiles * BLOCK_M) + t * BLOCK_M + row + pc.causal_off + 1 : 0x7fffffff;
+        const int tile_end = kCausal ? pc.mt * (kTiles * BLOCK_M) + t * BLOCK_M + pc.causal_off + 1 : 0x7fffffff;
+        const bool ragged = (k_len % BLOCK_N) != 0;
+        const int b_lo = pc.b_lo, nb_group = pc.nb_group;
+        // block jl of the piece (group block b_lo + jl) holds a key some row of this tile must not see (warp-uniform)
+        auto needs_mask = [&](int jl) { return (ragged && b_lo + jl + 1 == nb_group) || (b_lo + jl + 1) * BLOCK_N > tile_end; };
+        uint32_t sa[BLOCK_N], sb[BLOCK_N];
+        float m_blk;
+        auto mask_tail = [&](uint32_t(&x)[BLOCK_N], int jl) {
+          const int rem = min(k_len, row_end) - (b_lo + jl) * BLOCK_N;
 #pragma unroll
-            for (int c = 0; c < BLOCK_N; ++c)
-              if (c >= rem) sc[c] = 0xff800000u;  // -inf
-          }
-          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int c = 0; c < BLOCK_N; c += 8) {
-            mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(sc[c + 0]), __uint_as_float(sc[c + 1])));
-            mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(sc[c + 2]), __uint_as_float(sc[c + 3])));
-            mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(sc[c + 4]), __uint_as_float(sc[c + 5])));
-            mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(sc[c + 6]), __uint_as_float(sc[c + 7])));
-          }
-          const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+          for (int c = 0; c < BLOCK_N; ++c)
+            if (c >= rem) x[c] = 0xff800000u;  // -inf
+        };
+        auto max8 = [&](float* mx, const uint32_t(&x)[BLOCK_N], int gq) {
+          mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(x[gq * 8 + 0]), __uint_as_float(x[gq * 8 + 1])));
+          mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(x[gq * 8 + 2]), __uint_as_float(x[gq * 8 + 3])));
+          mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(x[gq * 8 + 4]), __uint_as_float(x[gq * 8 + 5])));
+          mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(x[gq * 8 + 6]), __uint_as_float(x[gq * 8 + 7])));
+        };
+
+        // cur: scores of block j (masked, max known in m_blk); nxt: receives block j+1.
+        // kHasNext: block j+1 exists; kMaskNext: it needs a mask.
+        auto body = [&](int j, uint32_t(&cur)[BLOCK_N], uint32_t(&nxt)[BLOCK_N], auto has_next_tag, auto mask_next_tag) {
+          constexpr bool kHasNext = decltype(has_next_tag)::value;
+          constexpr bool kMaskNext = decltype(mask_next_tag)::value;
+          const uint32_t gj = g + j;
+          const uint32_t p_addr = tmem + lane_base + tmem_s(t, gj & 1);
+          const float m_new = fmaxf(m_used, m_blk);
           if (j == 0) {
             m_used = m_new;
           } else {
             const bool need = (m_new - m_used) * scale_log2 > kRescaleThreshold;
             if (__any_sync(0xffffffffu, need)) {
-              mbar_wait(&bars->pv_done[t], (j - 1) & 1);
+              // rare: O_t must be complete up to P_t(j-1) V_{j-1} before it is rescaled in place; P_t(j)
+              // has not been released yet, so no later MMA can be touching O_t.
+              mbar_wait(&bars->pv_done[t], (gj - 1) & 1);
               tc_fence_after();
               const float alpha = need ? fast_exp2((m_used - m_new) * scale_log2) : 1.f;
               if (need) {
@@ -1029,19 +808,58 @@ __global__ void __launch_bounds__((kSplit == 1 || kSplit == 3) ? kThreadsSplit :
             }
           }
           const float neg_mc = -m_used * scale_log2;
-          const uint64_t scale2 = pack_f2(scale_log2, scale_log2), neg2 = pack_f2(neg_mc, neg_mc);
-          uint64_t ps2[2] = {0ull, 0ull};
           uint32_t pk[BLOCK_N / 2];
+          const uint64_t scale2 = pack_f2(scale_log2, scale_log2), neg2 = pack_f2(neg_mc, neg_mc);
+          uint64_t ps2[2] = {0ull, 0ull};  // packed row sums
+          auto exp8 = [&](int gq) {        // in place: score -> p
 #pragma unroll
-          for (int c = 0; c < BLOCK_N; c += 2) {
-            float x0, x1;
-            unpack_f2(ffma2(pack_f2(__uint_as_float(sc[c]), __uint_as_float(sc[c + 1])), scale2, neg2), x0, x1);
-            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-            ps2[(c >> 1) & 1] = fadd2(ps2[(c >> 1) & 1], pack_f2(p0, p1));
-            pk[c >> 1] = pack2<T>(p0, p1);
+            for (int c = 0; c < 8; c += 2) {
+              float x0, x1;
+              unpack_f2(ffma2(pack_f2(__uint_as_float(cur[gq * 8 + c]), __uint_as_float(cur[gq * 8 + c + 1])), scale2, neg2), x0, x1);
+              cur[gq * 8 + c] = __float_as_uint(fast_exp2(x0));
+              cur[gq * 8 + c + 1] = __float_as_uint(fast_exp2(x1));
+            }
+          };
+          auto sum_pack8 = [&](int gq) {
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+              const float p0 = __uint_as_float(cur[gq * 8 + c]), p1 = __uint_as_float(cur[gq * 8 + c + 1]);
+              ps2[(c >> 1) & 1] = fadd2(ps2[(c >> 1) & 1], pack_f2(p0, p1));
+              pk[(gq * 8 + c) >> 1] = pack2<T>(p0, p1);
+            }
+          };
+#pragma unroll
+          for (int gq = 0; gq < 6; ++gq) {
+            exp8(gq);
+            if (gq >= 2) sum_pack8(gq - 2);
           }
-          HG_TMEM_ST16(s_addr, pk, 0);
-          HG_TMEM_ST16(s_addr + 16, pk, 16);
+          HG_TMEM_ST16(p_addr, pk, 0);  // keys 0..31 of P
+          if constexpr (kHasNext) {     // S_t(j+1) has had ~3/4 of this block's MUFU time to land
+            mbar_wait(&bars->s_full[t][(gj + 1) & 1], ((gj + 1) >> 1) & 1);
+            tc_fence_after();
+            const uint32_t s_addr = tmem + lane_base + tmem_s(t, (gj + 1) & 1);
+            HG_TMEM_LD32(s_addr + 0, nxt, 0);
+            HG_TMEM_LD32(s_addr + 32, nxt, 32);
+          }
+          exp8(6);
+          sum_pack8(4);
+          exp8(7);
+          sum_pack8(5);
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          if constexpr (kHasNext) {
+            tmem_wait_ld();
+            if constexpr (kMaskNext) mask_tail(nxt, j + 1);
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) max8(mx, nxt, gq);
+          }
+          sum_pack8(6);
+          sum_pack8(7);
+          HG_TMEM_ST16(p_addr + 16, pk, 16);
+          if constexpr (kHasNext) {
+#pragma unroll
+            for (int gq = 4; gq < 8; ++gq) max8(mx, nxt, gq);
+            m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          }
           {
             float a0, a1;
             unpack_f2(fadd2(ps2[0], ps2[1]), a0, a1);
@@ -1049,234 +867,232 @@ __global__ void __launch_bounds__((kSplit == 1 || kSplit == 3) ? kThreadsSplit :
           }
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&bars->p_full[t][b]);
-        }
-      } else {
-      uint32_t sa[BLOCK_N], sb[BLOCK_N];
-      float m_blk;
-      auto mask_tail = [&](uint32_t(&x)[BLOCK_N], int j) {
-        const int rem = min(k_len, row_end) - j * BLOCK_N;
-#pragma unroll
-        for (int c = 0; c < BLOCK_N; ++c)
-          if (c >= rem) x[c] = 0xff800000u;  // -inf
-      };
-      auto max8 = [&](float* mx, const uint32_t(&x)[BLOCK_N], int g) {
-        mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(x[g * 8 + 0]), __uint_as_float(x[g * 8 + 1])));
-        mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(x[g * 8 + 2]), __uint_as_float(x[g * 8 + 3])));
-        mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(x[g * 8 + 4]), __uint_as_float(x[g * 8 + 5])));
-        mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(x[g * 8 + 6]), __uint_as_float(x[g * 8 + 7])));
-      };
+          mbar_arrive(&bars->p_full[t][gj & 1]);
+        };
 
-      // cur: scores of block j (masked, max known in m_blk); nxt: receives block j+1.
-      // kHasNext: block j+1 exists; kMaskNext: it is the ragged last block.
-      auto body = [&](int j, uint32_t(&cur)[BLOCK_N], uint32_t(&nxt)[BLOCK_N], auto has_next_tag, auto mask_next_tag) {
-        constexpr bool kHasNext = decltype(has_next_tag)::value;
-        constexpr bool kMaskNext = decltype(mask_next_tag)::value;
-        const uint32_t p_addr = tmem + lane_base + tmem_s(t, j & 1);
-        if (wq == 0 && lane == 0) HG_TRACE(1 + t, j, 1);
-        const float m_new = fmaxf(m_used, m_blk);
-        if (j == 0) {
-          m_used = m_new;
-        } else {
-          const bool need = (m_new - m_used) * scale_log2 > kRescaleThreshold;
-          if (__any_sync(0xffffffffu, need)) {
-            // rare: O_t must be complete up to P_t(j-1) V_{j-1} before it is rescaled in place; P_t(j)
-            // has not been released yet, so no later MMA can be touching O_t.
-            mbar_wait(&bars->pv_done[t], (j - 1) & 1);
-            tc_fence_after();
-            const float alpha = need ? fast_exp2((m_used - m_new) * scale_log2) : 1.f;
-            if (need) {
-              m_used = m_new;
-              l *= alpha;
+        {  // prologue: scores and row max of the piece's first block
+          mbar_wait(&bars->s_full[t][g & 1], (g >> 1) & 1);
+          HG_PTRACE(t == 0 && row == 0, first_piece ? 3 : 6);
+          tc_fence_after();
+          const uint32_t s_addr = tmem + lane_base + tmem_s(t, g & 1);
+          HG_TMEM_LD32(s_addr + 0, sa, 0);
+          HG_TMEM_LD32(s_addr + 32, sa, 32);
+          tmem_wait_ld();
+          if (needs_mask(0)) mask_tail(sa, 0);
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int gq = 0; gq < 8; ++gq) max8(mx, sa, gq);
+          m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        }
+        for (int j = 0; j < n; ++j) {
+          const bool last = j + 1 == n, mask_next = !last && needs_mask(j + 1);
+          if ((j & 1) == 0) {
+            if (last) body(j, sa, sb, std::false_type{}, std::false_type{});
+            else if (mask_next) body(j, sa, sb, std::true_type{}, std::true_type{});
+            else body(j, sa, sb, std::true_type{}, std::false_type{});
+          } else {
+            if (last) body(j, sb, sa, std::false_type{}, std::false_type{});
+            else if (mask_next) body(j, sb, sa, std::true_type{}, std::true_type{});
+            else body(j, sb, sa, std::true_type{}, std::false_type{});
+          }
+        }
+        mbar_wait(&bars->o_full[t], np & 1);
+        tc_fence_after();
+      }
+
+      // ---- epilogue of the piece -----------------------------------------------------------------
+      HG_PTRACE(t == 0 && row == 0, first_piece ? 4 : 7);
+      const int tile_row0 = pc.q_row0 + t * BLOCK_M;
+      T* const out = reinterpret_cast<T*>(P.lv[pc.level].out);
+      float* const lse = P.lv[pc.level].lse;
+      float m_log2 = n > 0 ? m_used * scale_log2 : -INFINITY;  // reference max of this piece's exponentials, log2 units
+      // A split unit: which CTAs hold its pieces, and which one am I?
+      //   2 pieces (the common case: a cut of the stream-K schedule falls inside the unit): the CTA of the HEAD piece
+      //     -- its last piece -- owns the unit: it folds the tail piece's partial (written long ago: a tail piece is
+      //     the first thing its CTA does) into its own accumulator, still in TMEM, and finishes the unit as if whole.
+      //   more pieces (few units on many SMs: the head-parallel ranks of a TP run): every piece leaves a partial and
+      //     the pieces' CTAs merge the unit together after their main work, each a slice of the rows (below).
+      bool to_workspace = false;
+      if (pc.split) {
+        int other = 0;
+        const int role = split_role(S, pc.unit, blockIdx.x, &other);
+        if (role == 1) {
+          const uint32_t* flag = ws_flags + kWsWordFlags + other * 2 + t;
+          while ((int32_t)(ld_acquire_gpu(flag) - epoch) < 0) {
+          }
+          const float* slot = P.ws_part + (int64_t)other * ws_slot_floats(D);
+          const float2 ml = ld_cg_f2(slot + ws_ml_index(D, t, row));
+          if (__any_sync(0xffffffffu, ml.y > 0.f)) {
+            // O_t <- w_own * O_t + w_part * partial, in place in TMEM (n > 0 here: the head piece of a unit whose tail
+            // holds keys holds keys itself); the normal epilogue below then finishes the unit
+            const float m_all = fmaxf(m_log2, ml.y > 0.f ? ml.x : -INFINITY);
+            const float w_own = fast_exp2(m_log2 - m_all), w_part = ml.y > 0.f ? fast_exp2(ml.x - m_all) : 0.f;
+            l = w_own * l + w_part * ml.y;
+            m_log2 = m_all;
+            float4 pa[8], pb[8];
+            auto fetch = [&](float4(&dst)[8], int c0) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) dst[c] = ld_cg_f4(slot + ws_o_index(D, t, row, (c0 >> 2) + c));
+            };
+            auto fold = [&](const float4(&src)[8], int c0) {
+              uint32_t o[32];
+              HG_TMEM_LD32(o_addr + c0, o, 0);
+              tmem_wait_ld();
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                o[4 * c + 0] = __float_as_uint(__uint_as_float(o[4 * c + 0]) * w_own + src[c].x * w_part);
+                o[4 * c + 1] = __float_as_uint(__uint_as_float(o[4 * c + 1]) * w_own + src[c].y * w_part);
+                o[4 * c + 2] = __float_as_uint(__uint_as_float(o[4 * c + 2]) * w_own + src[c].z * w_part);
+                o[4 * c + 3] = __float_as_uint(__uint_as_float(o[4 * c + 3]) * w_own + src[c].w * w_part);
+              }
+              HG_TMEM_ST32(o_addr + c0, o, 0);
+            };
+            fetch(pa, 0);
+#pragma unroll
+            for (int c0 = 0; c0 < D; c0 += 64) {
+              fetch(pb, c0 + 32);
+              fold(pa, c0);
+              if (c0 + 64 < D) fetch(pa, c0 + 64);
+              fold(pb, c0 + 32);
             }
+            tmem_wait_st();
+          }
+        } else {
+          to_workspace = true;
+          if (role == 2) duty_unit[pc.slot] = pc.unit;
+        }
+      }
+      if (to_workspace) {
+        // Partial result -> workspace slot of this CTA: unnormalised O row (fp32), then (max in log2 units, row sum).
+        // An empty piece leaves sum = 0 and is skipped by whoever merges.
+        float* slot = P.ws_part + (int64_t)(blockIdx.x * 2 + pc.slot) * ws_slot_floats(D);
+        if (n > 0) {
+#pragma unroll
+          for (int c0 = 0; c0 < D; c0 += 32) {
+            uint32_t o[32];
+            HG_TMEM_LD32(o_addr + c0, o, 0);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; c += 4)
+              *reinterpret_cast<uint4*>(slot + ws_o_index(D, t, row, (c0 + c) >> 2)) = make_uint4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+          }
+          tc_fence_before();
+          mbar_arrive(&bars->o_empty[t]);
+          if (row == 0) mbar_arrive(&bars->q_empty[t]);  // every MMA of the piece is complete: Q_t is dead
+        }
+        *reinterpret_cast<float2*>(slot + ws_ml_index(D, t, row)) = make_float2(m_log2, n > 0 ? l : 0.f);
+        __threadfence();
+        if (t == 0) named_bar_sync<1, BLOCK_M>(); else named_bar_sync<2, BLOCK_M>();
+        if (row == 0) st_release_gpu(ws_flags + kWsWordFlags + (blockIdx.x * 2 + pc.slot) * 2 + t, epoch);
+      } else {
+        const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+        auto final8 = [&](const uint32_t(&o)[32], int c) {  // columns c .. c + 8 of the chunk -> normalised 16-bit
+          uint4 w;
+          w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+          w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+          w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+          w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+          return w;
+        };
+        if (n > 0 && rows_valid == BLOCK_M) {
+          // full tile: rows -> the (dead) Q_t tile in the TMA 128-byte swizzle -> one bulk store per
+          // 64-column half.  Row r keeps 16-byte chunk c at chunk slot c ^ (r & 7).
+          uint8_t* stage = smem + L::kQ + t * L::kQTileBytes;
+#pragma unroll
+          for (int c0 = 0; c0 < D; c0 += 32) {
+            uint32_t o[32];
+            HG_TMEM_LD32(o_addr + c0, o, 0);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+              const int chunk = (c0 + c) >> 3;  // 16-byte chunk of the row
+              uint8_t* dst = stage + (chunk >> 3) * L::kQHalfBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+              *reinterpret_cast<uint4*>(dst) = final8(o, c);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&bars->o_empty[t]);
+          fence_proxy_async();
+          if (t == 0) named_bar_sync<1, BLOCK_M>(); else named_bar_sync<2, BLOCK_M>();
+          if (row == 0) {
+#pragma unroll
+            for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&P.tmap_o[pc.level], stage + h * L::kQHalfBytes, pc.head * D + h * 64, tile_row0);
+            bulk_commit();
+            bulk_wait_read();  // the staging tile has been read: the producer may load the next Q_t over it
+            mbar_arrive(&bars->q_empty[t]);
+          }
+        } else {
+          const bool row_ok = row < rows_valid;
+          T* orow = out + ((int64_t)(tile_row0 + row) * hq + pc.head) * D;
+          if (n > 0) {
 #pragma unroll
             for (int c0 = 0; c0 < D; c0 += 32) {
               uint32_t o[32];
               HG_TMEM_LD32(o_addr + c0, o, 0);
               tmem_wait_ld();
+              if (row_ok) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-              HG_TMEM_ST32(o_addr + c0, o, 0);
+                for (int c = 0; c < 32; c += 8) st_v4(orow + c0 + c, final8(o, c));
+              }
             }
+            tc_fence_before();
+            mbar_arrive(&bars->o_empty[t]);
+            if (row == 0) mbar_arrive(&bars->q_empty[t]);
+          } else if (row_ok) {  // a group without keys: out = 0 (lse = -inf below)
+#pragma unroll
+            for (int c = 0; c < D; c += 8) st_v4(orow + c, make_uint4(0, 0, 0, 0));
           }
         }
-        const float neg_mc = -m_used * scale_log2;
-        uint32_t pk[BLOCK_N / 2];
-        const uint64_t scale2 = pack_f2(scale_log2, scale_log2), neg2 = pack_f2(neg_mc, neg_mc);
-        uint64_t ps2[2] = {0ull, 0ull};  // packed row sums
-        auto exp8 = [&](int g) {  // in place: score -> p; every kEmuEvery-th pair goes to the FMA pipes
-#pragma unroll
-          for (int c = 0; c < 8; c += 2) {
-            float x0, x1;
-            unpack_f2(ffma2(pack_f2(__uint_as_float(cur[g * 8 + c]), __uint_as_float(cur[g * 8 + c + 1])), scale2, neg2), x0, x1);
-            float p0, p1;
-            if (kEmuEvery > 0 && ((c >> 1) % kEmuEvery) == kEmuEvery - 1) {
-              exp2_poly_x2(x0, x1, p0, p1);
-            } else {
-              p0 = fast_exp2(x0);
-              p1 = fast_exp2(x1);
-            }
-            cur[g * 8 + c] = __float_as_uint(p0);
-            cur[g * 8 + c + 1] = __float_as_uint(p1);
-          }
-        };
-        auto sum_pack8 = [&](int g) {
-#pragma unroll
-          for (int c = 0; c < 8; c += 2) {
-            const float p0 = __uint_as_float(cur[g * 8 + c]), p1 = __uint_as_float(cur[g * 8 + c + 1]);
-            ps2[(c >> 1) & 1] = fadd2(ps2[(c >> 1) & 1], pack_f2(p0, p1));
-            pk[(g * 8 + c) >> 1] = pack2<T>(p0, p1);
-          }
-        };
-#pragma unroll
-        for (int g = 0; g < 6; ++g) {
-          exp8(g);
-          if (g >= 2) sum_pack8(g - 2);
-        }
-        HG_TMEM_ST16(p_addr, pk, 0);  // keys 0..31 of P
-        if (wq == 0 && lane == 0) HG_TRACE(1 + t, j, 2);
-        if constexpr (kHasNext) {     // S_t(j+1) has had ~3/4 of this block's MUFU time to land
-          mbar_wait(&bars->s_full[t][(j + 1) & 1], ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          const uint32_t s_addr = tmem + lane_base + tmem_s(t, (j + 1) & 1);
-          HG_TMEM_LD32(s_addr + 0, nxt, 0);
-          HG_TMEM_LD32(s_addr + 32, nxt, 32);
-        }
-        if (wq == 0 && lane == 0) HG_TRACE(1 + t, j, 3);
-        exp8(6);
-        sum_pack8(4);
-        exp8(7);
-        sum_pack8(5);
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if constexpr (kHasNext) {
-          tmem_wait_ld();
-          if constexpr (kMaskNext) mask_tail(nxt, j + 1);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) max8(mx, nxt, g);
-        }
-        sum_pack8(6);
-        sum_pack8(7);
-        HG_TMEM_ST16(p_addr + 16, pk, 16);
-        if constexpr (kHasNext) {
-#pragma unroll
-          for (int g = 4; g < 8; ++g) max8(mx, nxt, g);
-          m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        }
-        {
-          float a0, a1;
-          unpack_f2(fadd2(ps2[0], ps2[1]), a0, a1);
-          l += a0 + a1;
-        }
-        if (wq == 0 && lane == 0) HG_TRACE(1 + t, j, 4);
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&bars->p_full[t][j & 1]);
-        if (wq == 0 && lane == 0) HG_TRACE(1 + t, j, 5);
-      };
-
-      // Phase offset between the two tiles: their softmax warps share one MUFU unit per SM sub-partition, and left
-      // alone they run in lock-step (both in their exp phase, then both outside it).  Starting tile B part of a
-      // block later lets one tile's exponentials run behind the other's TMEM / barrier latencies.
-      // (b_delay: below, after the first scores have arrived.  Measured at cfg#2, r01i: 0 -> 33.0 us, 400 -> 32.9,
-      // 600 -> 32.4, 800 -> 32.2, 1000 -> 32.7, 1300 -> 33.3; no effect at B = 4096.  Short prefixes skip it.)
-      {  // prologue: scores and row max of block 0
-        if (wq == 0 && lane == 0) HG_TRACE(1 + t, 0, 0);
-        mbar_wait(&bars->s_full[t][0], 0);
-        if (t == 1 && b_delay > 0 && n_blocks >= 16) {  // counted from the moment the first scores are there
-          const long long t_start = clock64();
-          while (clock64() - t_start < (long long)b_delay) {
-          }
-        }
-        tc_fence_after();
-        const uint32_t s_addr = tmem + lane_base + tmem_s(t, 0);
-        HG_TMEM_LD32(s_addr + 0, sa, 0);
-        HG_TMEM_LD32(s_addr + 32, sa, 32);
-        tmem_wait_ld();
-        if (needs_mask(0)) mask_tail(sa, 0);
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int g = 0; g < 8; ++g) max8(mx, sa, g);
-        m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        if (row < rows_valid && lse != nullptr)
+          lse[(int64_t)(tile_row0 + row) * hq + pc.head] = (l > 0.f) ? (m_log2 + fast_log2(l)) * kLn2 : -INFINITY;
       }
-      for (int j = 0; j < n_blocks; ++j) {
-        const bool last = j + 1 == n_blocks, mask_next = !last && needs_mask(j + 1);
-        if ((j & 1) == 0) {
-          if (last) body(j, sa, sb, std::false_type{}, std::false_type{});
-          else if (mask_next) body(j, sa, sb, std::true_type{}, std::true_type{});
-          else body(j, sa, sb, std::true_type{}, std::false_type{});
-        } else {
-          if (last) body(j, sb, sa, std::false_type{}, std::false_type{});
-          else if (mask_next) body(j, sb, sa, std::true_type{}, std::true_type{});
-          else body(j, sb, sa, std::true_type{}, std::false_type{});
-        }
+      HG_PTRACE(t == 0 && row == 0, first_piece ? 5 : 8);
+      first_piece = false;
+      if (n > 0) {
+        g += n;
+        ++np;
       }
-      }  // pipelined form
-
-      // ---- epilogue --------------------------------------------------------------------------
-      mbar_wait(&bars->o_full[t], 0);
-      tc_fence_after();
-      const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
-      const int tile_row0 = q_row0 + t * BLOCK_M;
-      if (rows_valid == BLOCK_M) {
-        // full tile: O_t / l -> the (dead) Q_t tile in the TMA 128-byte swizzle -> one bulk store per
-        // 64-column half.  Row r keeps 16-byte chunk c at chunk slot c ^ (r & 7).
-        uint8_t* stage = smem + L::kQ + t * L::kQTileBytes;
-#pragma unroll
-        for (int c0 = 0; c0 < D; c0 += 32) {
-          uint32_t o[32];
-          HG_TMEM_LD32(o_addr + c0, o, 0);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            uint4 w;
-            w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
-            w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
-            w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
-            w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
-            const int chunk = (c0 + c) >> 3;  // 16-byte chunk of the row
-            uint8_t* dst = stage + (chunk >> 3) * L::kQHalfBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = w;
-          }
-        }
-        fence_proxy_async();
-        if (t == 0) named_bar_sync<1, BLOCK_M>(); else named_bar_sync<2, BLOCK_M>();
-        if (wq == 0 && lane == 0) {
-#pragma unroll
-          for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&tmap_o, stage + h * L::kQHalfBytes, head * D + h * 64, split * n_q_rows + tile_row0);
-          bulk_commit_and_wait();
-        }
-      } else {
-        const bool row_ok = row < rows_valid;
-        T* orow = out + ((int64_t)(tile_row0 + row) * hq + head) * D;
-#pragma unroll
-        for (int c0 = 0; c0 < D; c0 += 32) {
-          uint32_t o[32];
-          HG_TMEM_LD32(o_addr + c0, o, 0);
-          tmem_wait_ld();
-          if (row_ok) {
-#pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-              uint4 w;
-              w.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
-              w.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
-              w.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
-              w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
-              st_v4(orow + c0 + c, w);
-            }
-          }
-        }
-      }
-      if (row < rows_valid && lse != nullptr)
-        lse[(int64_t)(tile_row0 + row) * hq + head] = (l > 0.f) ? (m_used * scale_log2 + fast_log2(l)) * kLn2 : -INFINITY;
-      tc_fence_before();
     }
+
+    // ---- merge duty (units cut into more than two pieces): this CTA's share of the rows -----------------------
+    // (the pieces of one unit finish at about the same time on their CTAs -- every CTA's range has the same cost -- so
+    // the flags polled here are already up or about to be; nothing below depends on a CTA that is itself waiting)
+    if (ws_flags != nullptr) {
+      for (int dty = 0; dty < 2; ++dty) {
+        const int unit = duty_unit[dty];
+        if (unit < 0 || (dty == 1 && unit == duty_unit[0])) continue;
+        SchedPiece su;
+        sched_decode_unit(S, unit, su);
+        su.b_lo = su.b_hi = su.split = su.slot = 0;
+        Piece pu;
+        resolve_piece<kCausal>(P, su, pu);
+        merge_duty<T, D>(S, P.ws_part, ws_flags, epoch, unit, (warp - 4) * 32 + lane, lane, reinterpret_cast<T*>(P.lv[pu.level].out),
+                         P.lv[pu.level].lse, pu.q_row0, min(kTiles * BLOCK_M, pu.rows_left), pu.head, hq);
+      }
+    }
+    HG_PTRACE(t == 0 && row == 0, 9);
+    if (row == 0) bulk_wait_all();  // this thread's TMA stores have reached global memory before the grid retires
+    tc_fence_before();
   }
 
   // ---- teardown ----------------------------------------------------------------------------
   __syncthreads();
+  HG_PTRACE(threadIdx.x == 0, 10);
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+  if (threadIdx.x == 0 && P.ws_flags != nullptr) {
+    // last CTA out: the next launch on this workspace sees the next epoch (it reads it after griddepcontrol.wait,
+    // i.e. after this grid has retired)
+    uint32_t* f = P.ws_flags;
+    const uint32_t e = *reinterpret_cast<volatile uint32_t*>(f + kWsWordEpoch);
+    __threadfence();
+    if (atomicAdd(f + kWsWordExit, 1u) == gridDim.x - 1) {
+      f[kWsWordExit] = 0u;
+      __threadfence();
+      f[kWsWordEpoch] = e + 1u;
+    }
   }
 }
 
@@ -1302,37 +1118,41 @@ static int make_tmap(CUtensorMap* map, const void* base, int dtype, uint64_t row
   return HG_OK;
 }
 
-// HYDRAGEN_B200_PREFIX_BDELAY (cycles, read once): start offset of tile B's softmax warps
-static int prefix_b_delay() {
-  static const int v = [] {
-    const char* e = getenv("HYDRAGEN_B200_PREFIX_BDELAY");
-    return e != nullptr ? atoi(e) : HG_PREFIX_BDELAY_DEFAULT;
-  }();
-  return v;
-}
-
-template <typename T, int D, bool kCausal, int kSplit>
-static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) {
+template <typename T, int D, bool kCausal>
+static int launch_prefix_inst(const PrefixParams& p, const SchedParams& sched, int dtype, cudaStream_t s) {
   using L = SmemLayout<D>;
-  const int64_t n_q_rows = (int64_t)p.n_groups * p.q_per_group;
-  CUtensorMap tq, tk, tv, to;
+  PrefixKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
   int rc;
-  if ((rc = make_tmap(&tq, p.q, dtype, n_q_rows, (uint64_t)p.hq * D, p.q_stride_row, BLOCK_M)) != HG_OK) return rc;
-  if ((rc = make_tmap(&tk, p.k, dtype, p.n_k_rows, (uint64_t)p.hkv * D, p.kv_stride_row, BLOCK_N)) != HG_OK) return rc;
-  if ((rc = make_tmap(&tv, p.v, dtype, p.n_k_rows, (uint64_t)p.hkv * D, p.kv_stride_row, BLOCK_N)) != HG_OK) return rc;
-  const int splits = p.kv_splits < 1 ? 1 : p.kv_splits;
-  if ((rc = make_tmap(&to, p.out, dtype, n_q_rows * splits, (uint64_t)p.hq * D, (uint64_t)p.hq * D, BLOCK_M)) != HG_OK) return rc;
-  const int smem_bytes = L::kTotal + 1024;
-  static bool attr_set = false;  // per instantiation; idempotent, racing threads set the same value
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(prefix_attn_sm100_kernel<T, D, kCausal, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return set_error(HG_ERR_CUDA, "prefix: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+  if ((rc = make_tmap(&kp.tmap_q, p.q, dtype, (uint64_t)p.n_q_rows, (uint64_t)p.hq * D, (uint64_t)p.q_stride_row, BLOCK_M)) != HG_OK) return rc;
+  for (int l = 0; l < p.n_levels; ++l) {
+    const PrefixLevel& lv = p.levels[l];
+    if ((rc = make_tmap(&kp.tmap_k[l], lv.k, dtype, (uint64_t)lv.n_k_rows, (uint64_t)p.hkv * D, (uint64_t)lv.kv_stride_row, BLOCK_N)) != HG_OK) return rc;
+    if ((rc = make_tmap(&kp.tmap_v[l], lv.v, dtype, (uint64_t)lv.n_k_rows, (uint64_t)p.hkv * D, (uint64_t)lv.kv_stride_row, BLOCK_N)) != HG_OK) return rc;
+    if ((rc = make_tmap(&kp.tmap_o[l], lv.out, dtype, (uint64_t)p.n_q_rows, (uint64_t)p.hq * D, (uint64_t)p.hq * D, BLOCK_M)) != HG_OK) return rc;
+    kp.lv[l].out = lv.out;
+    kp.lv[l].lse = lv.lse;
+    kp.lv[l].cu = lv.cu_seqlens_k;
+    kp.lv[l].k_len = lv.k_len;
   }
-  const int tiles_per_group = (p.q_per_group + kTiles * BLOCK_M - 1) / (kTiles * BLOCK_M);
+  kp.sched = sched;
+  kp.hkv = p.hkv;
+  kp.scale_log2 = p.scale_log2;
+  if (sched.mode == 0) {
+    kp.ws_flags = reinterpret_cast<uint32_t*>(p.workspace);
+    kp.ws_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + kWsFlagBytes);
+  }
+  const int smem_bytes = L::kTotal + 1024;
+  static bool attr_set[64] = {};  // per instantiation and device; idempotent, racing threads set the same value
+  const int dev = device_info().device;
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(prefix_attn_sm100_kernel<T, D, kCausal>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return set_error(HG_ERR_CUDA, "prefix: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(p.n_groups * tiles_per_group * splits), (unsigned)p.hq, 1);
-  cfg.blockDim = dim3((kSplit == 1 || kSplit == 3) ? kThreadsSplit : kThreads);
+  cfg.gridDim = dim3((unsigned)sched.n_ctas, 1, 1);
+  cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -1340,8 +1160,7 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, prefix_attn_sm100_kernel<T, D, kCausal, kSplit>, tq, tk, tv, to, (T*)p.out, p.lse, p.cu_seqlens_k, p.q_per_group,
-                                     tiles_per_group, p.k_len, p.hq, p.hkv, p.scale_log2, splits, (int)n_q_rows, prefix_b_delay());
+  cudaError_t e = cudaLaunchKernelEx(&cfg, prefix_attn_sm100_kernel<T, D, kCausal>, kp);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(HG_ERR_CUDA, "prefix_attn_sm100: launch failed: %s", cudaGetErrorString(e));
@@ -1349,115 +1168,117 @@ static int launch_prefix_inst(const PrefixParams& p, int dtype, cudaStream_t s) 
   return check_launch("prefix_attn_sm100");
 }
 
-#if !defined(HG_PREFIX_TU_CAUSAL) && !defined(HG_PREFIX_TU_SPLIT) && !defined(HG_PREFIX_TU_SIMPLE) && !defined(HG_PREFIX_TU_ALT)
+#if !defined(HG_PREFIX_TU_CAUSAL)
+
 #ifdef HG_PREFIX_TRACE
-extern "C" int hg_debug_read_trace(long long* host_buf, int n) {
+extern "C" int hg_debug_prefix_trace(long long* host_buf, int n) {
   cudaDeviceSynchronize();
-  return (int)cudaMemcpyFromSymbol(host_buf, g_trace, sizeof(long long) * (size_t)n);
+  return (int)cudaMemcpyFromSymbol(host_buf, g_prefix_trace, sizeof(long long) * (size_t)n);
 }
 #endif
 
-// Number of KV splits that brings the CTA count of a prefix launch close to the SM count without going
-// below 4 key blocks per CTA: the head-parallel ranks of a tensor-parallel run own few heads each.
-int suggest_prefix_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits) {
-  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
-  const long long base = (long long)n_groups * ((q_per_group + kTiles * BLOCK_M - 1) / (kTiles * BLOCK_M)) * hq;
-  if (base <= 0) return 1;
-  const int n_blocks = (max_k_len + BLOCK_N - 1) / BLOCK_N;
-  int s = (int)(sms / base);
-  s = min(s, n_blocks / 4);
-  s = min(s, max_splits);
-  return s < 1 ? 1 : s;
-}
+int64_t prefix_workspace_bytes() { return ws_bytes(128); }
 
-int launch_prefix_causal(const PrefixParams& p, int dtype, cudaStream_t s);  // prefix_sm100_causal.cu
-int launch_prefix_split(const PrefixParams& p, int dtype, cudaStream_t s);   // prefix_sm100_split.cu
-int launch_prefix_simple(const PrefixParams& p, int dtype, cudaStream_t s);  // prefix_sm100_simple.cu
-int launch_prefix_alt(const PrefixParams& p, int dtype, cudaStream_t s);     // prefix_sm100_alt.cu
-
-// HYDRAGEN_B200_PREFIX_SOFTMAX = base | split | simple | alt (read once): which softmax organisation the non-causal
-// launches use (0 base: software pipelined, the default; 1 split-column; 2 simple: not pipelined; 3 alternate-block)
-static int softmax_variant() {
+// HYDRAGEN_B200_PREFIX_CTAS (development knob, read once): cap on the persistent grid (default: the SM count)
+static int prefix_cta_cap() {
   static const int v = [] {
-    const char* e = getenv("HYDRAGEN_B200_PREFIX_SOFTMAX");
-    if (e == nullptr) return HG_PREFIX_SOFTMAX_DEFAULT;
-    if (e[0] == 's' && e[1] == 'p') return 1;
-    if (e[0] == 's' && e[1] == 'i') return 2;
-    if (e[0] == 'a') return 3;
-    return 0;
+    const char* e = getenv("HYDRAGEN_B200_PREFIX_CTAS");
+    return e != nullptr ? atoi(e) : 0;
   }();
   return v;
 }
 
+// The schedule of one launch: levels laid end to end on the cost axis, grid sized so that every CTA gets at least one
+// minimal piece and no unit is cut into more pieces than the merge handles.
+int build_prefix_schedule(const PrefixParams& p, int n_sms, bool allow_split, SchedParams* out) {
+  SchedParams S;
+  memset(&S, 0, sizeof(S));
+  S.n_levels = p.n_levels;
+  S.hq = p.hq;
+  S.c0 = 2;         // prologue + epilogue of a unit, in key blocks (~1.6k cycles each)
+  S.min_piece = 4;  // no piece shorter than this many key blocks
+  long long cost = 0;
+  int units = 0, w_max = 1;
+  for (int l = 0; l < p.n_levels; ++l) {
+    const PrefixLevel& lv = p.levels[l];
+    SchedLevel& L = S.lv[l];
+    if (lv.n_groups < 1 || p.n_q_rows % lv.n_groups != 0)
+      return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: level %d: %d groups do not divide %lld query rows", l, lv.n_groups, (long long)p.n_q_rows);
+    L.n_groups = lv.n_groups;
+    L.q_per_group = (int)(p.n_q_rows / lv.n_groups);
+    L.tiles_per_group = (L.q_per_group + kTiles * BLOCK_M - 1) / (kTiles * BLOCK_M);
+    const int kmax = lv.cu_seqlens_k != nullptr ? lv.max_k_len : lv.k_len;
+    L.nb_max = (kmax + BLOCK_N - 1) / BLOCK_N;
+    const long long nu = (long long)L.n_groups * L.tiles_per_group * p.hq;
+    if (nu + units > 0x3fffffffLL) return set_error(HG_ERR_UNSUPPORTED, "prefix: too many work units");
+    L.n_units = (int)nu;
+    L.unit0 = units;
+    L.cost0 = cost;
+    units += L.n_units;
+    cost += nu * (L.nb_max + S.c0);
+    if (L.nb_max + S.c0 > w_max) w_max = L.nb_max + S.c0;
+  }
+  S.total_units = units;
+  S.total_cost = cost;
+  int cap = n_sms > 0 ? n_sms : 148;
+  if (cap > kMaxCtas) cap = kMaxCtas;
+  if (prefix_cta_cap() > 0 && prefix_cta_cap() < cap) cap = prefix_cta_cap();
+  if (allow_split) {
+    S.mode = 0;
+    long long g = cap;
+    g = std::min<long long>(g, std::max<long long>(1, cost / (S.c0 + S.min_piece)));
+    // pieces per unit <= w_max / (cost / g) + 2  must stay within kMaxUnitPieces
+    g = std::min<long long>(g, std::max<long long>(1, (long long)(kMaxUnitPieces - 3) * cost / w_max));
+    S.n_ctas = (int)std::max<long long>(1, g);
+  } else {
+    S.mode = 1;
+    S.n_ctas = std::max(1, std::min(cap, units));
+  }
+  *out = S;
+  return HG_OK;
+}
+
+int launch_prefix_causal(const PrefixParams& p, const SchedParams& sched, int dtype, cudaStream_t s);  // prefix_sm100_causal.cu
+
 int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
-  if (p.n_groups == 0 || p.q_per_group == 0) return HG_OK;
+  if (p.n_levels < 1 || p.n_levels > kMaxLevels) return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: %d shared levels (1..%d)", p.n_levels, kMaxLevels);
+  if (p.n_q_rows == 0) return HG_OK;
   if (dtype != HG_F16 && dtype != HG_BF16)
     return set_error(HG_ERR_UNSUPPORTED, "prefix: the tcgen05 kernel takes f16/bf16 only (dtype %d)", dtype);
-  if (p.q_stride_row % 8 != 0 || p.kv_stride_row % 8 != 0 || reinterpret_cast<uintptr_t>(p.q) % 16 != 0 ||
-      reinterpret_cast<uintptr_t>(p.k) % 16 != 0 || reinterpret_cast<uintptr_t>(p.v) % 16 != 0 ||
-      reinterpret_cast<uintptr_t>(p.out) % 16 != 0)
-    return set_error(HG_ERR_UNSUPPORTED, "prefix: TMA needs 16-byte aligned bases and row strides");
-  if (p.hq > 65535) return set_error(HG_ERR_UNSUPPORTED, "prefix: hq > 65535");
+  if (p.q_stride_row % 8 != 0 || reinterpret_cast<uintptr_t>(p.q) % 16 != 0) return set_error(HG_ERR_UNSUPPORTED, "prefix: TMA needs 16-byte aligned bases and row strides");
+  for (int l = 0; l < p.n_levels; ++l) {
+    const PrefixLevel& lv = p.levels[l];
+    if (lv.kv_stride_row % 8 != 0 || reinterpret_cast<uintptr_t>(lv.k) % 16 != 0 || reinterpret_cast<uintptr_t>(lv.v) % 16 != 0 ||
+        reinterpret_cast<uintptr_t>(lv.out) % 16 != 0)
+      return set_error(HG_ERR_UNSUPPORTED, "prefix: TMA needs 16-byte aligned bases and row strides");
+  }
+  if (p.d != 64 && p.d != 128) return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
   if (p.causal) {
-    if (p.cu_seqlens_k != nullptr || p.kv_splits > 1 || p.k_len < p.q_per_group)
-      return set_error(HG_ERR_UNSUPPORTED, "prefix: the causal form takes uniform groups with k_len >= q rows per group and no kv split");
-    return launch_prefix_causal(p, dtype, s);
+    const PrefixLevel& lv = p.levels[0];
+    if (p.n_levels != 1 || lv.cu_seqlens_k != nullptr || lv.k_len < p.n_q_rows / lv.n_groups)
+      return set_error(HG_ERR_UNSUPPORTED, "prefix: the causal form takes one level of uniform groups with k_len >= q rows per group");
   }
-  if (softmax_variant() == 1) return launch_prefix_split(p, dtype, s);
-  if (softmax_variant() == 2) return launch_prefix_simple(p, dtype, s);
-  if (softmax_variant() == 3) return launch_prefix_alt(p, dtype, s);
+  const bool allow_split = !p.causal && p.workspace != nullptr && p.workspace_bytes >= ws_bytes(p.d);
+  SchedParams sched;
+  int rc = build_prefix_schedule(p, device_info().sm_count, allow_split, &sched);
+  if (rc != HG_OK) return rc;
+  sched.heavy_first = p.causal ? 1 : 0;
+  if (p.causal) return launch_prefix_causal(p, sched, dtype, s);
   if (dtype == HG_BF16) {
-    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false, 0>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, false, 0>(p, dtype, s);
-  } else {
-    if (p.d == 128) return launch_prefix_inst<__half, 128, false, 0>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__half, 64, false, 0>(p, dtype, s);
+    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false>(p, sched, dtype, s);
+    return launch_prefix_inst<__nv_bfloat16, 64, false>(p, sched, dtype, s);
   }
-  return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
+  if (p.d == 128) return launch_prefix_inst<__half, 128, false>(p, sched, dtype, s);
+  return launch_prefix_inst<__half, 64, false>(p, sched, dtype, s);
 }
-#elif defined(HG_PREFIX_TU_CAUSAL)  // second translation unit: the causal instantiations (compiled in parallel)
-int launch_prefix_causal(const PrefixParams& p, int dtype, cudaStream_t s) {
+#else  // second translation unit: the causal instantiations (compiled in parallel)
+int launch_prefix_causal(const PrefixParams& p, const SchedParams& sched, int dtype, cudaStream_t s) {
   if (dtype == HG_BF16) {
-    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, true, 0>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, true, 0>(p, dtype, s);
-  } else {
-    if (p.d == 128) return launch_prefix_inst<__half, 128, true, 0>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__half, 64, true, 0>(p, dtype, s);
+    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, true>(p, sched, dtype, s);
+    return launch_prefix_inst<__nv_bfloat16, 64, true>(p, sched, dtype, s);
   }
-  return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
-}
-#elif defined(HG_PREFIX_TU_ALT)  // fifth translation unit: the alternate-block softmax instantiations
-int launch_prefix_alt(const PrefixParams& p, int dtype, cudaStream_t s) {
-  if (dtype == HG_BF16) {
-    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false, 3>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, false, 3>(p, dtype, s);
-  } else {
-    if (p.d == 128) return launch_prefix_inst<__half, 128, false, 3>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__half, 64, false, 3>(p, dtype, s);
-  }
-  return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
-}
-#elif defined(HG_PREFIX_TU_SIMPLE)  // fourth translation unit: the non-pipelined softmax instantiations
-int launch_prefix_simple(const PrefixParams& p, int dtype, cudaStream_t s) {
-  if (dtype == HG_BF16) {
-    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false, 2>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, false, 2>(p, dtype, s);
-  } else {
-    if (p.d == 128) return launch_prefix_inst<__half, 128, false, 2>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__half, 64, false, 2>(p, dtype, s);
-  }
-  return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
-}
-#else  // HG_PREFIX_TU_SPLIT: third translation unit: the split-column softmax instantiations
-int launch_prefix_split(const PrefixParams& p, int dtype, cudaStream_t s) {
-  if (dtype == HG_BF16) {
-    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false, 1>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__nv_bfloat16, 64, false, 1>(p, dtype, s);
-  } else {
-    if (p.d == 128) return launch_prefix_inst<__half, 128, false, 1>(p, dtype, s);
-    if (p.d == 64) return launch_prefix_inst<__half, 64, false, 1>(p, dtype, s);
-  }
-  return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
+  if (p.d == 128) return launch_prefix_inst<__half, 128, true>(p, sched, dtype, s);
+  return launch_prefix_inst<__half, 64, true>(p, sched, dtype, s);
 }
 #endif
 

@@ -21,7 +21,7 @@ permuted VIEW of the ``[b, sq, h]`` buffer the kernels write, so the reference's
 from __future__ import annotations
 
 import os
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -40,6 +40,11 @@ def _causal_backend() -> str:
 def _prefix_backend() -> str:
     """'auto' (default), 'tcgen05' or 'rowwise' -- test hook, read per call."""
     return os.environ.get("HYDRAGEN_B200_PREFIX_BACKEND", "auto")
+
+
+def _prefix_split() -> bool:
+    """HYDRAGEN_B200_PREFIX_SPLIT=0: never cut a (group, tile, head) unit between CTAs (test hook, read per call)."""
+    return os.environ.get("HYDRAGEN_B200_PREFIX_SPLIT", "1") != "0"
 
 
 def _rows_view(t: Tensor) -> Optional[int]:
@@ -84,88 +89,102 @@ def prefix_attention_grouped(
     cu_seqlens_k: Optional[Tensor] = None,
     max_seqlen_k: Optional[int] = None,
 ) -> Tuple[Tensor, Tensor]:
-    outs, lses = prefix_attention_partials(q, k, v, n_groups, cu_seqlens_k, max_seqlen_k, max_splits=1)
+    """The prefix branch of ONE shared level: ``q [b, nq, hq, d]`` with the batch grouped contiguously by shared
+    parent (``b % n_groups == 0``), ``k, v`` either ``[n_groups, L, hkv, d]`` or, with ``cu_seqlens_k`` (int32
+    ``[n_groups + 1]`` on device), packed ``[total, hkv, d]``.  Returns ``out [b, nq, hq, d]`` and ``lse [b, nq, hq]``
+    (fp32) -- already in the layout the combine consumes (hydragen/attention.py:276-280, 333-338 need no transpose)."""
+    outs, lses = prefix_attention_levels(q, [k], [v], [n_groups], [cu_seqlens_k], [max_seqlen_k])
     return outs[0], lses[0]
 
 
-def prefix_attention_partials(
-    q: Tensor,
-    k: Tensor,
-    v: Tensor,
-    n_groups: int,
-    cu_seqlens_k: Optional[Tensor] = None,
-    max_seqlen_k: Optional[int] = None,
-    max_splits: int = 1,
-):
-    """``prefix_attention_grouped`` as a list of partial results: when the launch has too few (group, tile,
-    head) work items to fill the GPU -- the head-parallel ranks of a tensor-parallel run -- the keys are cut
-    into up to ``max_splits`` ranges (split-KV) and one ``(out, lse)`` pair per range is returned, to be
-    merged by the combine that follows anyway.  Returns (list of out, list of lse).
-    Each ``out [b, nq, hq, d]`` / ``lse [b, nq, hq]`` (fp32) is already in the layout the
-    combine consumes (hydragen/attention.py:276-280, 333-338 need no transpose here).
+def prefix_attention_partials(q, k, v, n_groups, cu_seqlens_k=None, max_seqlen_k=None, max_splits: int = 1):
+    """Round-1 name: the prefix branch as a LIST of partial results.  Split-KV now happens inside the persistent
+    kernel (stream-K pieces merged in the launch itself), so the list always holds one entry."""
+    out, lse = prefix_attention_grouped(q, k, v, n_groups, cu_seqlens_k, max_seqlen_k)
+    return [out], [lse]
 
-    The prefix branch proper: ``q [b, nq, hq, d]`` with the batch grouped contiguously by shared
-    parent (``b % n_groups == 0``), ``k, v`` either ``[n_groups, L, hkv, d]`` or, with
-    ``cu_seqlens_k`` (int32 ``[n_groups + 1]`` on device), packed ``[total, hkv, d]``."""
+
+def prefix_attention_levels(
+    q: Tensor,
+    shared_ks: Sequence[Tensor],
+    shared_vs: Sequence[Tensor],
+    n_groups: Sequence[int],
+    cu_seqlens: Sequence[Optional[Tensor]],
+    max_seqlens: Sequence[Optional[int]],
+):
+    """The prefix branch of EVERY shared level of a hierarchy (the loop of hydragen/attention.py:250-341) in one
+    persistent tcgen05 launch: returns ``(outs, lses)``, one ``[b, nq, hq, d]`` / ``[b, nq, hq]`` pair per level.
+    fp32 inputs and head dims the tensor-core kernel does not take run level by level on the CUDA-core kernel."""
     b, nq, hq, d = q.shape
-    if n_groups < 1 or b % n_groups != 0:
-        raise ValueError(f"batch {b} is not a multiple of the number of shared sequences {n_groups}")
-    hkv = k.shape[-2]
+    n_levels = len(shared_ks)
+    if not (len(shared_vs) == len(n_groups) == len(cu_seqlens) == len(max_seqlens) == n_levels):
+        raise ValueError("one entry per shared level is needed in every list")
+    if n_levels == 0:
+        return [], []
     sm_scale = d**-0.5  # hydragen/flash.py:293
     backend = _prefix_backend()
     use_tc = q.dtype in _TC_DTYPES and d in _TC_HEAD_DIMS and backend != "rowwise"
     if backend == "tcgen05" and not use_tc:
         raise ValueError(f"tcgen05 prefix kernel does not take dtype {q.dtype} / head_dim {d}")
-    varlen = cu_seqlens_k is not None
-    if varlen:
-        if k.ndim != 3:
-            raise ValueError("varlen shared K/V must be [total, kvheads, d]")
-        if cu_seqlens_k.dtype != torch.int32 or cu_seqlens_k.shape[0] != n_groups + 1:
-            raise ValueError("cu_seqlens_k must be int32 of n_groups + 1 entries")
-    splits = 1
-    if use_tc and max_splits > 1:
-        k_max = int(max_seqlen_k) if (varlen and max_seqlen_k is not None) else (k.shape[0] if varlen else k.shape[1])
-        splits = _lib.prefix_suggest_splits(q.device, n_groups, (b // n_groups) * nq, hq, k_max, max_splits)
-    out = torch.empty((splits, b, nq, hq, d), device=q.device, dtype=q.dtype)
-    lse = torch.empty((splits, b, nq, hq), device=q.device, dtype=torch.float32)
+    hkv = shared_ks[0].shape[-2]
+    outs = [torch.empty((b, nq, hq, d), device=q.device, dtype=q.dtype) for _ in range(n_levels)]
+    lses = [torch.empty((b, nq, hq), device=q.device, dtype=torch.float32) for _ in range(n_levels)]
+    q_rs = None
     if use_tc:
         q_rs = _rows_view(q)
         if q_rs is None:
             q = q.contiguous()
             q_rs = hq * d
+    elif not _inner_ok(q):
+        q = q.contiguous()
+    descs, keep = [], []
+    for i in range(n_levels):
+        k, v, ng, cu, mx = shared_ks[i], shared_vs[i], int(n_groups[i]), cu_seqlens[i], max_seqlens[i]
+        if ng < 1 or b % ng != 0:
+            raise ValueError(f"batch {b} is not a multiple of the number of shared sequences {ng}")
+        if k.shape != v.shape or k.shape[-2] != hkv or k.shape[-1] != d or k.dtype != q.dtype or v.dtype != q.dtype:
+            raise ValueError(f"shared K/V of level {i}: shapes {tuple(k.shape)} / {tuple(v.shape)}, dtypes {k.dtype} / {v.dtype}")
+        varlen = cu is not None
         if varlen:
-            if not (k.stride(2) == 1 and k.stride(1) == d and v.stride() == k.stride()):
-                k, v = k.contiguous(), v.contiguous()
-            n_k_rows, k_len, kv_rs = k.shape[0], 0, k.stride(0)
-            max_k = int(max_seqlen_k) if max_seqlen_k is not None else k.shape[0]
+            if k.ndim != 3:
+                raise ValueError("varlen shared K/V must be [total, kvheads, d]")
+            if cu.dtype != torch.int32 or cu.shape[0] != ng + 1:
+                raise ValueError("cu_seqlens_k must be int32 of n_groups + 1 entries")
+        elif k.ndim != 4 or k.shape[0] != ng:
+            raise ValueError(f"shared K/V must be [n_groups, L, kvheads, d], got {tuple(k.shape)}")
+        if use_tc:
+            if varlen:
+                if not (k.stride(2) == 1 and k.stride(1) == d and v.stride() == k.stride()):
+                    k, v = k.contiguous(), v.contiguous()
+                n_k_rows, k_len, kv_rs = k.shape[0], 0, k.stride(0)
+                max_k = int(mx) if mx is not None else k.shape[0]
+            else:
+                kv_rs = _rows_view(k)
+                if kv_rs is None or _rows_view(v) != kv_rs:
+                    k, v = k.contiguous(), v.contiguous()
+                    kv_rs = hkv * d
+                n_k_rows, k_len = k.shape[0] * k.shape[1], k.shape[1]
+                max_k = 0
+            keep += [k, v]
+            descs.append(_lib.make_prefix_level(k, v, outs[i], lses[i], cu, n_k_rows, kv_rs, ng, k_len, max_k))
         else:
-            if k.ndim != 4 or k.shape[0] != n_groups:
-                raise ValueError(f"shared K/V must be [n_groups, L, kvheads, d], got {tuple(k.shape)}")
-            kv_rs = _rows_view(k)
-            if kv_rs is None or _rows_view(v) != kv_rs:
-                k, v = k.contiguous(), v.contiguous()
-                kv_rs = hkv * d
-            n_k_rows, k_len = k.shape[0] * k.shape[1], k.shape[1]
-            max_k = k_len
-        _lib.prefix_attn_fwd(q, k, v, out, lse, n_groups, (b // n_groups) * nq, n_k_rows, k_len, cu_seqlens_k, max_k,
-                             hq, hkv, d, q_rs, kv_rs, sm_scale, kv_splits=splits)
-    else:
-        # CUDA-core path (fp32, other head dims): every sequence walks its parent's keys.
-        if not _inner_ok(q):
-            q = q.contiguous()
-        if not _inner_ok(k):
-            k = k.contiguous()
-        if not _inner_ok(v) or v.stride() != k.stride():
-            v = v.contiguous()
-            k = k.contiguous()
-        if varlen:
-            strides = (0, k.stride(0), k.stride(1))
-            lk = int(max_seqlen_k) if max_seqlen_k is not None else k.shape[0]
-        else:
-            strides = (k.stride(0), k.stride(1), k.stride(2))
-            lk = k.shape[1]
-        _lib.rowwise_attn_fwd(q, k, v, None, cu_seqlens_k, b // n_groups, False, out[0], lse[0], lk, strides, [], [], sm_scale)
-    return [out[i] for i in range(splits)], [lse[i] for i in range(splits)]
+            # CUDA-core path (fp32, other head dims): every sequence walks its parent's keys.
+            if not _inner_ok(k):
+                k = k.contiguous()
+            if not _inner_ok(v) or v.stride() != k.stride():
+                v = v.contiguous()
+                k = k.contiguous()
+            if varlen:
+                strides = (0, k.stride(0), k.stride(1))
+                lk = int(mx) if mx is not None else k.shape[0]
+            else:
+                strides = (k.stride(0), k.stride(1), k.stride(2))
+                lk = k.shape[1]
+            _lib.rowwise_attn_fwd(q, k, v, None, cu, b // ng, False, outs[i], lses[i], lk, strides, [], [], sm_scale)
+    # one launch covers up to MAX_PREFIX_LEVELS levels (deeper hierarchies: one launch per chunk of levels)
+    for i in range(0, len(descs), _lib.MAX_PREFIX_LEVELS):
+        _lib.prefix_attn_grouped_fwd(q, b * nq, q_rs, descs[i : i + _lib.MAX_PREFIX_LEVELS], hq, hkv, d, sm_scale, split=_prefix_split())
+    return outs, lses
 
 
 def flash_attention(q: Tensor, k: Tensor, v: Tensor, causal: bool = False) -> Tuple[Tensor, Tensor]:

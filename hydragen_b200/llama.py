@@ -122,34 +122,53 @@ class LlamaMLP(nn.Module):
 
 
 class HydragenLlamaRotaryEmbedding(nn.Module):
-    """cos/sin tables for half-split RoPE (emb = cat(freqs, freqs)); ``rows(position_ids)`` returns
-    the table rows for absolute positions, shaped to broadcast over the head axis."""
+    """cos/sin tables for half-split RoPE (emb = cat(freqs, freqs)), hydragen/llama.py:47-55.
 
-    cos_cached: Tensor
-    sin_cached: Tensor
+    The tables are NOT module buffers: they are computed on first use, on the device they are asked for, in fp32
+    (exactly as the reference's buffers are: on CPU-independent arithmetic) and cached per (dtype, device).  A model
+    whose parameters were created on the ``meta`` device (``from_pretrained`` / ``from_pretrained_tp`` build the module
+    tree there before the checkpoint is assigned) therefore never owns a meta buffer that ``.to(device)`` would have
+    to copy -- the reference gets the same effect from ``init_empty_weights(include_buffers=False)``."""
 
     def __init__(self, dim: int, max_position_embeddings: int = 2048, base: float = 10000.0, scaling_factor: float = 1.0):
         super().__init__()
-        inv_freq = 1.0 / (base ** (torch.arange(0, dim, 2, dtype=torch.float32) / dim))
-        t = torch.arange(max_position_embeddings, dtype=torch.float32) / scaling_factor
-        freqs = torch.outer(t, inv_freq)
-        emb = torch.cat((freqs, freqs), dim=-1)
-        self.register_buffer("cos_cached", emb.cos(), persistent=False)
-        self.register_buffer("sin_cached", emb.sin(), persistent=False)
+        self.dim, self.max_position_embeddings, self.base, self.scaling_factor = dim, max_position_embeddings, float(base), float(scaling_factor)
+        self._fp32: dict = {}  # device -> (cos, sin) fp32 [max_pos, dim]
         self._cast: dict = {}  # (dtype, device) -> tables cast once
 
-    def forward(self, x: Tensor, seq_len=None):
-        """The full tables in the activation dtype (hydragen/llama.py:47-55).  The reference casts them on
-        every call (once per layer per step); here the cast copy is made once per dtype and kept."""
-        return self.tables(x.dtype)
+    def _tables_fp32(self, device: torch.device):
+        hit = self._fp32.get(device)
+        if hit is None:
+            # built on the CPU in fp32 and copied: identical bits on every device and rank
+            inv_freq = 1.0 / (self.base ** (torch.arange(0, self.dim, 2, dtype=torch.float32) / self.dim))
+            t = torch.arange(self.max_position_embeddings, dtype=torch.float32) / self.scaling_factor
+            freqs = torch.outer(t, inv_freq)
+            emb = torch.cat((freqs, freqs), dim=-1)
+            hit = (emb.cos().to(device), emb.sin().to(device))
+            self._fp32 = {device: hit}
+        return hit
 
-    def tables(self, dtype: torch.dtype):
-        key = (dtype, self.cos_cached.device)
+    @property
+    def cos_cached(self) -> Tensor:
+        return self._tables_fp32(torch.device("cpu"))[0]
+
+    @property
+    def sin_cached(self) -> Tensor:
+        return self._tables_fp32(torch.device("cpu"))[1]
+
+    def forward(self, x: Tensor, seq_len=None):
+        """The full tables in the activation dtype on ``x``'s device.  The reference casts them on every call (once
+        per layer per step); here the cast copy is made once per (dtype, device) and kept."""
+        return self.tables(x.dtype, x.device)
+
+    def tables(self, dtype: torch.dtype, device: Union[str, torch.device, None] = None):
+        device = torch.device(device) if device is not None else torch.device("cpu")
+        key = (dtype, device)
         hit = self._cast.get(key)
         if hit is None:
-            hit = (self.cos_cached.to(dtype=dtype).contiguous(), self.sin_cached.to(dtype=dtype).contiguous())
-            self._cast.clear()
-            self._cast[key] = hit
+            cos, sin = self._tables_fp32(device)
+            hit = (cos.to(dtype=dtype).contiguous(), sin.to(dtype=dtype).contiguous())
+            self._cast = {key: hit}
         return hit
 
 
@@ -196,6 +215,7 @@ class SharedCache(nn.Module):
         # varlen; the flag is kept because callers and the graph-invalidation logic read it.
         self.use_varlen = False
         self.sliced_sequence_length: Optional[int] = None
+        self.max_used_length = 0  # host copy of max(seq_lens) of the current fill (capacity checks without a device read)
 
     def get_current_batch_size(self) -> int:
         return self.current_batch_size
@@ -223,6 +243,7 @@ class SharedCache(nn.Module):
         self.cumsum_lengths[1 : bs + 1].copy_(seq_lens.cumsum(0).to(torch.int32))
         self.use_varlen = max(lens) != min(lens)
         self.sliced_sequence_length = None if self.use_varlen else lens[0]
+        self.max_used_length = max(lens)
         self.current_batch_size = bs
 
     def get_used_cumsum_lengths(self) -> Tensor:
@@ -486,7 +507,8 @@ class HydragenLlamaModel(nn.Module):
         self.rotary_emb = HydragenLlamaRotaryEmbedding(_cfg_head_dim(config), config.max_position_embeddings,
                                                        getattr(config, "rope_theta", 10000.0), factor)
         for layer in self.layers:
-            layer.self_attn.rotary_emb = self.rotary_emb  # plain attribute, as in the reference
+            # shared, and NOT registered as a submodule of every attention layer (the reference assigns a plain attribute too)
+            object.__setattr__(layer.self_attn, "rotary_emb", self.rotary_emb)
         self.mode: Optional[str] = None
 
     # -- switches and graph-validity probes (hydragen/llama.py:666-714) ---------------------------
@@ -523,7 +545,7 @@ class HydragenLlamaModel(nn.Module):
     # -- forward -----------------------------------------------------------------------------------
     def make_context(self, position_ids: Tensor, dtype: torch.dtype, valid_lens: Optional[Tensor] = None) -> StepContext:
         cache = self._attn().kv_cache
-        cos, sin = self.rotary_emb.tables(dtype)
+        cos, sin = self.rotary_emb.tables(dtype, position_ids.device)
         if self.get_disable_hydragen():
             upos = position_ids
         else:
@@ -651,13 +673,12 @@ class HydragenLlamaForCausalLM(nn.Module):
         hf_model = LlamaForCausalLM.from_pretrained(model_name_or_path, **kwargs)
         if hf_model.dtype not in (torch.float16, torch.bfloat16):
             raise ValueError(f"Model must be in float16 or bfloat16, not {hf_model.dtype}")
-        with torch.device("meta"):
+        with torch.device("meta"):  # parameters only: the module tree owns no buffers (see HydragenLlamaRotaryEmbedding)
             model = cls(hf_model.config)
-        sd = hf_model.state_dict()
-        sd = {k: v for k, v in sd.items() if "rotary_emb" not in k}
-        model.load_state_dict(sd, assign=True, strict=False)
-        model.model.rotary_emb = HydragenLlamaRotaryEmbedding(_cfg_head_dim(hf_model.config), hf_model.config.max_position_embeddings,
-                                                              getattr(hf_model.config, "rope_theta", 10000.0))
+        sd = {k: v for k, v in hf_model.state_dict().items() if "rotary_emb" not in k}
+        missing, unexpected = model.load_state_dict(sd, assign=True, strict=False)
+        if missing:
+            raise ValueError(f"checkpoint lacks parameters of the module tree: {missing[:5]}{' ...' if len(missing) > 5 else ''}")
         model.to(hf_model.device)
         model.device, model.dtype = hf_model.device, hf_model.dtype
         return model
@@ -780,6 +801,9 @@ class HydragenLlamaForCausalLM(nn.Module):
         """Prefill of per-sequence (non-shared) prompt tokens into the unique cache."""
         self.set_mode(AttentionMode.UNIQUE_PREFILL)
         bs, width = input_ids.shape
+        cache = self.model._attn().kv_cache
+        if bs > cache.per_completion_k_cache.shape[0] or width > cache.per_completion_k_cache.shape[1]:
+            raise ValueError(f"[{bs}, {width}] unique tokens exceed the unique cache {tuple(cache.per_completion_k_cache.shape[:2])} (setup_caches)")
         start = self.get_shared_cache_len(bs)
         pos = start[:, None] + torch.arange(width, device=input_ids.device, dtype=torch.long)[None, :]
         return self(input_ids=input_ids, position_ids=pos, seq_lens=seq_lens)
@@ -787,6 +811,24 @@ class HydragenLlamaForCausalLM(nn.Module):
     def repeat_per_completion_cache_for_num_samples(self, current_size: int, num_samples: int):
         for layer in self.model.layers:
             layer.self_attn.kv_cache.repeat_per_completion_cache_for_num_samples(current_size, num_samples)
+
+    def _check_capacity(self, batch: int, shared: List[Tensor], suffix: Optional[Tensor], max_new_tokens: int, disable_hydragen: bool):
+        """Fail loudly BEFORE anything is written when the request does not fit the caches or the RoPE tables (the
+        kernels clamp out-of-range rows instead of faulting; the reference's scatter_ / gather would raise).  Host
+        arithmetic on the padded widths -- upper bounds of the true lengths -- so there is no device read."""
+        cache = self.model._attn().kv_cache
+        cap_b, cap_len = cache.per_completion_k_cache.shape[0], cache.per_completion_k_cache.shape[1]
+        if batch > cap_b:
+            raise ValueError(f"{batch} sequences exceed max_unique_batch_size = {cap_b} (setup_caches)")
+        shared_len = sum(c.max_used_length for c in cache.get_used_shared_caches()) + sum(int(t.shape[1]) for t in shared)
+        suffix_w = int(suffix.shape[1]) if suffix is not None else 0
+        unique_rows = (shared_len if disable_hydragen else 0) + suffix_w + max(0, max_new_tokens - 1)
+        if unique_rows > cap_len:
+            raise ValueError(f"{unique_rows} tokens per sequence ({suffix_w} prompt + {max_new_tokens} new"
+                             f"{' + ' + str(shared_len) + ' copied shared' if disable_hydragen else ''}) exceed max_unique_seq_length = {cap_len} (setup_caches)")
+        max_pos = int(self.config.max_position_embeddings)
+        if shared_len + suffix_w + max(0, max_new_tokens - 1) > max_pos:
+            raise ValueError(f"positions up to {shared_len + suffix_w + max_new_tokens - 2} exceed max_position_embeddings = {max_pos} (RoPE table rows)")
 
     # -- generation ------------------------------------------------------------------------------
     @torch.no_grad()
@@ -855,6 +897,7 @@ class HydragenLlamaForCausalLM(nn.Module):
             shared, shared_lens, suffix, suffix_lens = levels, level_lens, None, None
         else:
             shared, shared_lens, suffix, suffix_lens = levels[:-1], level_lens[:-1], levels[-1], level_lens[-1]
+        self._check_capacity(batch, shared, suffix, max_new_tokens, disable_hydragen)
 
         logits = None if starting_logits is None else starting_logits.unsqueeze(1)
         for ids, lens in zip(shared, shared_lens):

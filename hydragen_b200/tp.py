@@ -19,6 +19,7 @@ launch per rank.  ``backend="gloo"`` (CPU) runs the same code in the unit tests.
 
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -54,39 +55,54 @@ def shard_state_dict(sd: Dict[str, Tensor], rank: int, world_size: int) -> Dict[
 
 
 class _AllReduce:
-    """Sum over the tensor-parallel group on the compute stream.  On CUDA with NVLink multicast the library's
-    NVLS kernel (csrc/allreduce.cu) on a symmetric staging buffer; otherwise ``torch.distributed.all_reduce``
-    (NCCL on GPUs without multicast, gloo in the CPU tests).  Shared by every layer of a model: one staging
-    buffer per message size, set up on first use (the warm-up runs before a CUDA-graph capture)."""
+    """Sum over the tensor-parallel group on the compute stream.  Messages up to ``NVLS_MAX_BYTES`` (the decode-step
+    ``[B, 1, hidden]`` sizes) go through the library's NVLS kernel (csrc/allreduce.cu) where the platform has NVLink
+    multicast; everything else -- prefill activations, whose shape changes with every prompt -- through
+    ``torch.distributed.all_reduce`` (NCCL; gloo in the CPU tests).
 
-    _nvls: Dict[tuple, object] = {}
+    ONE symmetric arena per process group, created on first use (every rank issues the same collectives in the same
+    order, so they all get here together) and never grown: two halves used alternately, so a result stays valid until
+    the second-next call.  Whether the NVLS path is used is AGREED across the ranks (a MIN all-reduce of "my set-up
+    worked"): a rank that fell back on its own would leave the others spinning in the kernel's flag barrier."""
+
+    NVLS_MAX_BYTES = int(os.environ.get("HYDRAGEN_B200_NVLS_MAX_MIB", "32")) << 20
+    _arenas: Dict[int, object] = {}  # id(group) -> [MultimemAllReduce, [half0, half1] uint8 views, turn] or None (agreed: not available)
 
     def __init__(self, group=None, use_nvls: bool = True):
         self.group = group
         self.use_nvls = use_nvls
 
-    def _staging(self, x: Tensor):
-        key = (x.device, x.dtype, tuple(x.shape), id(self.group))
-        if key not in _AllReduce._nvls:
-            entry = None
+    def _arena(self, device: torch.device):
+        key = id(self.group)
+        if key not in _AllReduce._arenas:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("the NVLS all-reduce must be set up before CUDA-graph capture (run one eager step first)")
+            entry, ok = None, 0
             try:
-                from .collectives import make_all_reduce
+                from .collectives import MultimemAllReduce
 
-                ar = make_all_reduce(x.numel() * x.element_size() + 256, x.device, self.group)
-                if ar is not None:
-                    entry = (ar, ar.buffer(tuple(x.shape), x.dtype))
-            except Exception:
-                entry = None
-            _AllReduce._nvls[key] = entry
-        return _AllReduce._nvls[key]
+                ar = MultimemAllReduce(2 * self.NVLS_MAX_BYTES + 512, device, self.group)
+                if ar.available:
+                    entry = [ar, [ar.buffer((self.NVLS_MAX_BYTES,), torch.uint8) for _ in range(2)], 0]  # collective, halves, whose turn
+                    ok = 1
+            except Exception as ex:  # no symmetric memory / no multicast on this platform
+                import warnings
+
+                warnings.warn(f"NVLS all-reduce unavailable on this rank ({ex!r}); the group will agree on NCCL")
+            flag = torch.tensor([ok], device=device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            _AllReduce._arenas[key] = entry if int(flag.item()) == 1 else None
+        return _AllReduce._arenas[key]
 
     def __call__(self, x: Tensor) -> Tensor:
-        if self.use_nvls and x.is_cuda and dist.get_backend(self.group) == "nccl":
-            entry = self._staging(x)
+        nbytes = x.numel() * x.element_size()
+        if (self.use_nvls and x.is_cuda and 0 < nbytes <= self.NVLS_MAX_BYTES and nbytes % 16 == 0 and x.dtype in (torch.bfloat16, torch.float16, torch.float32)
+                and dist.get_backend(self.group) == "nccl"):
+            entry = self._arena(x.device)
             if entry is not None:
-                ar, buf = entry
+                ar, halves, turn = entry
+                buf = halves[turn][:nbytes].view(x.dtype).view(x.shape)
+                entry[2] = turn ^ 1  # shared by every layer of the model: the arena, not the layer, alternates
                 buf.copy_(x)
                 ar.all_reduce_(buf)
                 return buf
@@ -154,22 +170,26 @@ def from_config_tp(config, dtype: torch.dtype = torch.bfloat16, device=None, see
     return model
 
 
-def from_pretrained_tp(model_name: str, load_dir, dtype: Optional[torch.dtype] = None):
-    """hydragen/tp.py:135-180: build the sharded module tree and load ``{load_dir}/{rank}.pt``."""
+def from_pretrained_tp(model_name: str, load_dir, dtype: Optional[torch.dtype] = None, device=None):
+    """hydragen/tp.py:135-180: build the sharded module tree and load ``{load_dir}/{rank}.pt`` (the files
+    ``shard_state_dict`` / the reference's ``make_tp_files.py`` produce).  ``device`` defaults to this rank's GPU."""
     from pathlib import Path
 
     from transformers import LlamaConfig as HFLlamaConfig
 
     config = HFLlamaConfig.from_pretrained(model_name)
     rank, world_size = get_rank(), get_world_size()
-    device = f"cuda:{rank}"
-    parts = sorted(Path(load_dir).glob("*.pt"))
+    if device is None:
+        device = f"cuda:{rank}" if torch.cuda.is_available() else "cpu"
+    parts = sorted(Path(load_dir).glob("*.pt"), key=lambda p: int(p.stem))
     assert len(parts) == world_size, f"{len(parts)} != {world_size}"
-    with torch.device("meta"):
+    with torch.device("meta"):  # parameters only: the module tree owns no buffers (HydragenLlamaRotaryEmbedding)
         model = HydragenLlamaForCausalLM(config)
         apply_tp(model.model, rank, world_size)
     sd = torch.load(parts[rank], map_location=device)
-    model.load_state_dict(sd, assign=True, strict=False)
+    missing, _ = model.load_state_dict(sd, assign=True, strict=False)
+    if missing:
+        raise ValueError(f"{parts[rank]} lacks parameters of the sharded module tree: {missing[:5]}{' ...' if len(missing) > 5 else ''}")
     model.to(device)
     model.device = device
     if dtype is None or dtype == "auto":

@@ -10,7 +10,7 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in
  *     `_host` ; the library never allocates, frees or retains device memory (the caller owns
- *     outputs and workspace) and never synchronises: all work is enqueued on `stream`
+ *     outputs and the workspace) and never synchronises: all work is enqueued on `stream`
  *     (a cudaStream_t passed as void*), so every entry point is CUDA-graph capturable.
  *   - return value: 0 on success, negative hg_status otherwise; hg_last_error() returns a
  *     thread-local message.  No C++ exception crosses the boundary.
@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HG_ABI_VERSION 1
+#define HG_ABI_VERSION 2
 #define HG_MAX_COMBINE 8 /* max partial results merged by one call (shared levels + suffix) */
 
 typedef enum hg_dtype {
@@ -113,48 +113,69 @@ int hg_rowwise_attn_fwd(const void* q, const void* k, const void* v, const void*
 /* ---------------------------------------------------------------------------------------
  * Shared-prefix attention on the 5th-generation tensor cores (tcgen05.mma, accumulators in
  * TMEM, operands staged by TMA): all sequences that share a prefix are batched into one Q
- * matrix per head and multiplied against the ONE copy of that prefix's K/V.
- * Replaces flash_attention (hydragen/flash.py:284-306 -> flash-attn _flash_attn_forward, called
- * from hydragen/attention.py:270) and flash_attention_varlen (flash.py:309-351, called from
- * attention.py:313) together with the LSE transposes that follow them (attention.py:276-280,
- * 333-338): the kernel writes the LSE directly in [b, nq, hq].
+ * matrix per head and multiplied against the ONE copy of that prefix's K/V -- for EVERY shared
+ * level of a hierarchy in one persistent launch.
+ * Replaces, per level, flash_attention (hydragen/flash.py:284-306 -> flash-attn _flash_attn_forward, called
+ * from hydragen/attention.py:270) or flash_attention_varlen (flash.py:309-351, called from
+ * attention.py:313) together with the LSE transpose that follows it (attention.py:276-280,
+ * 333-338): the kernel writes each level's LSE directly in [b, nq, hq].  (The reference loops over the
+ * levels in Python, attention.py:250-341: one library launch + one transpose per level.)
  *
- *   q      [n_q_rows, hq, d] with row stride q_stride_row (elements), rows grouped contiguously
- *          by shared parent: group g owns rows [g*q_per_group, (g+1)*q_per_group)
- *          (n_q_rows = n_groups * q_per_group = b * nq; the "(n s) nq -> n (s nq)" batching of
- *          attention.py:264-268 is this view).
- *   k, v   [n_k_rows, hkv, d] with row stride kv_stride_row; group g owns rows
- *          [g*k_len, (g+1)*k_len) when cu_seqlens_k == NULL, else [cu[g], cu[g+1]) with
- *          cu_seqlens_k an int32 DEVICE array of n_groups+1 entries read by the kernel (no host
- *          sync, unlike SharedCache.fill's .item(), hydragen/llama.py:158-163) and max_k_len an
- *          upper bound on any group's length.
- *   out    [n_q_rows, hq, d] contiguous (dtype);  lse [n_q_rows, hq] fp32 (may be NULL).
- * dtype HG_F16 or HG_BF16; d 64 or 128; hq % hkv == 0.  n_k_rows bounds the TMA descriptor:
- * rows past it read as zero.
+ *   q      [n_q_rows, hq, d] with row stride q_stride_row (elements); n_q_rows = b * nq.
+ *   levels_host  HOST array of n_levels (1..4) descriptors (copied into the launch).  Level i splits the query
+ *          rows into n_groups contiguous groups of n_q_rows / n_groups rows ("(n s) nq -> n (s nq)",
+ *          attention.py:264-268); group g attends to
+ *            rows [g*k_len, (g+1)*k_len) of k, v              when cu_seqlens_k == NULL,
+ *            rows [cu_seqlens_k[g], cu_seqlens_k[g+1])         otherwise (int32 DEVICE array of n_groups+1
+ *          entries read by the kernel -- no host sync, unlike SharedCache.fill's .item(), hydragen/llama.py:158-163;
+ *          max_k_len = an upper bound on any group's length, used to balance the schedule),
+ *          k, v [n_k_rows, hkv, d] with row stride kv_stride_row (rows past n_k_rows read as zero), and writes
+ *          out [n_q_rows, hq, d] contiguous (dtype), lse [n_q_rows, hq] fp32 (may be NULL): the level's
+ *          partial result, in the layout hg_combine_lse / hg_decode_attn_fused consume.
+ *   workspace    hg_prefix_workspace_bytes() bytes of device memory, zero-initialised ONCE by the caller and
+ *          then owned by the library's launches: the persistent CTAs (one per SM) cut the (unit, key block)
+ *          space of all levels into equal ranges (stream-K), and a unit cut between CTAs leaves fp32
+ *          partial accumulators and flags there, merged inside the same launch.  Launches that may run
+ *          concurrently need separate workspaces; launches on one stream share one.  NULL: units are never
+ *          cut (whole (group, 256-row tile, head) units are dealt round-robin) -- correct, but a launch
+ *          with few units then leaves SMs idle.
+ * dtype HG_F16 or HG_BF16; d 64 or 128; hq % hkv == 0.
  */
+typedef struct hg_prefix_level {
+  const void* k;
+  const void* v;
+  void* out;
+  float* lse;
+  const int32_t* cu_seqlens_k;
+  int64_t n_k_rows;
+  int64_t kv_stride_row;
+  int32_t n_groups;
+  int32_t k_len;     /* uniform key count per group (cu_seqlens_k == NULL) */
+  int32_t max_k_len; /* ragged levels: upper bound of any group's key count (0: n_k_rows) */
+  int32_t reserved;
+} hg_prefix_level;
+
+int hg_prefix_attn_grouped_fwd(const void* q, int64_t n_q_rows, int64_t q_stride_row,
+                               const hg_prefix_level* levels_host, int n_levels, int hq, int hkv, int d,
+                               float sm_scale, int dtype, void* workspace, int64_t workspace_bytes,
+                               void* stream);
+
+/* Bytes of workspace hg_prefix_attn_grouped_fwd / hg_prefix_attn_fwd want (independent of the problem). */
+int64_t hg_prefix_workspace_bytes(void);
+
+/* One level (the non-hierarchical case): group g owns query rows [g*q_per_group, (g+1)*q_per_group). */
 int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
                        int n_groups, int q_per_group, int64_t n_k_rows, int k_len,
                        const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
                        int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype,
-                       void* stream);
+                       void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Split-KV form of hg_prefix_attn_fwd for launches with few (group, m-tile, head) work items -- the
- * head-parallel ranks of a tensor-parallel run (hydragen/tp.py:90-112) own Hq/N heads each: the keys of
- * every group are cut into kv_splits contiguous ranges, each handled by its own CTAs, and kv_splits
- * PARTIAL results are written back to back:
- *   out [kv_splits, n_q_rows, hq, d],  lse [kv_splits, n_q_rows, hq]   (a split with no keys: out 0, lse -inf)
- * to be merged by hg_combine_lse / the n_partials of hg_rowwise_attn_fwd / hg_decode_attn_fused (this is
- * flash-attn's split-KV, whose heuristic the reference copies in hydragen/flash.py:37-73, with the reduce
- * folded into the combine that follows anyway).  kv_splits == 1 is hg_prefix_attn_fwd. */
-int hg_prefix_attn_split_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
-                             int n_groups, int q_per_group, int64_t n_k_rows, int k_len,
-                             const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
-                             int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype,
-                             int kv_splits, void* stream);
-
-/* Suggested kv_splits (>= 1, <= max_splits) for a prefix launch on the device seen by hg_init:
- * fills the SMs without going below 4 key blocks per CTA.  Host-side arithmetic only. */
-int hg_prefix_suggest_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits);
+/* Host-side view of the work schedule such a launch would use on a device with n_sms SMs (no device access;
+ * pointers inside levels_host are ignored, a level is ragged iff max_k_len > 0).  Writes up to max_pieces
+ * records of 10 int32 {cta, unit, level, head, group, row tile, first key block, end key block, split, slot}
+ * and the grid size; returns the number of pieces (negative hg_status on error).  For tests and tooling. */
+int hg_prefix_schedule(const hg_prefix_level* levels_host, int n_levels, int64_t n_q_rows, int hq, int n_sms,
+                       int allow_split, int32_t* pieces_out, int max_pieces, int32_t* n_ctas_out);
 
 /* ---------------------------------------------------------------------------------------
  * Causal self-attention of a prefill chunk on the tensor cores: the same tcgen05 kernel with a bottom-right
@@ -215,8 +236,11 @@ int hg_decode_attn_fused(const void* q, const void* k_new, const void* v_new, co
  *              else a private (non-symmetric) output buffer of nbytes: one-shot (every rank reduces the whole
  *              message through the switch; one barrier) -- the input buffer may be overwritten only after a
  *              later call of either form has completed
- *   flags_dev  DEVICE array of `world` pointers: flags_dev[p] = rank p's flag array (uint32, zero-initialised
- *              once, >= n_blocks * world entries), reachable through NVLink peer access
+ *   flags_dev  DEVICE array of `world` pointers: flags_dev[p] = rank p's flag array (>= 128 uint32 words,
+ *              zero-initialised once, never touched by the host afterwards), reachable through NVLink peer
+ *              access.  Word 0 counts the collectives a rank has completed (the epoch); words 32+p / 64+p hold
+ *              the epoch at which rank p announced "input in place" / "slice written everywhere" -- peers
+ *              write them with one st.release.sys each, every rank polls only its own copy
  *   nbytes     message size, a multiple of 16;  n_blocks  CTAs to use (the same on every rank, <= SM count)
  * Every rank of the group must enqueue the same call in the same order.  CUDA-graph capturable. */
 int hg_allreduce_multimem(void* mc_ptr, void* out, const void* flags_dev, int rank, int world,

@@ -1,6 +1,7 @@
-"""Development aid: per-block clock64 timeline of one prefix-kernel CTA (needs a build with
-HG_EXTRA_NVCC_FLAGS=-DHG_PREFIX_TRACE, which goes to hydragen_b200/_C_dev).  Run under gpurun:
-    HG_EXTRA_NVCC_FLAGS=-DHG_PREFIX_TRACE python scripts/trace_prefix.py"""
+"""Development aid (1 GPU; library built with HG_EXTRA_NVCC_FLAGS=-DHG_PREFIX_TRACE and the same variable set at run time):
+%globaltimer stamps of the persistent prefix kernel's stages per CTA, for the last launch of a graph of back-to-back
+launches at cfg#2 (or TP_B / TP_L / TP_H): where a CTA's time goes -- set-up, wait for the previous grid, first scores,
+main loop, epilogue, merge, exit."""
 import ctypes
 import os
 import sys
@@ -11,28 +12,35 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hydragen_b200 import _lib  # noqa: E402
 from hydragen_b200.flash import prefix_attention_grouped  # noqa: E402
 
-lib = _lib.load()
-B, L, H, D = int(os.environ.get("TRACE_B", "1024")), 2048, 32, 128
-q = torch.randn(B, 1, H, D, device="cuda", dtype=torch.bfloat16)
-k = torch.randn(1, L, H, D, device="cuda", dtype=torch.bfloat16)
-v = torch.randn(1, L, H, D, device="cuda", dtype=torch.bfloat16)
-for _ in range(3):
-    prefix_attention_grouped(q, k, v, n_groups=1)
+B, Lp, H, D, NL = int(os.environ.get("TP_B", "1024")), int(os.environ.get("TP_L", "2048")), int(os.environ.get("TP_H", "32")), 128, 8
+q = [torch.randn(B, 1, H, D, device="cuda", dtype=torch.bfloat16) for _ in range(NL)]
+k = [torch.randn(1, Lp, H, D, device="cuda", dtype=torch.bfloat16) for _ in range(NL)]
+v = [torch.randn(1, Lp, H, D, device="cuda", dtype=torch.bfloat16) for _ in range(NL)]
+
+
+def run():
+    for i in range(NL):
+        prefix_attention_grouped(q[i], k[i], v[i], n_groups=1)
+
+
+run()
 torch.cuda.synchronize()
-n = 3 * 64 * 8
-buf = (ctypes.c_longlong * n)()
-lib.hg_debug_read_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
-rc = lib.hg_debug_read_trace(buf, n)
-assert rc == 0, rc
-tr = [[[buf[(r * 64 + j) * 8 + s] for s in range(8)] for j in range(64)] for r in range(3)]
-nb = (L + 63) // 64
-t0 = min(x for x in tr[1][0][:2] if x > 0)
-print("MMA warp A: j | wait_kv wait_p issue+commit | iter start")
-for j in range(min(nb, 32)):
-    m = tr[0][j]
-    print(f"{j:3d} | {m[1]-m[0]:6d} {m[2]-m[1]:6d} {m[3]-m[2]:6d} | {m[0]-t0:7d}")
-for r, nm in ((1, "A"), (2, "B")):
-    print(f"softmax {nm}: j | exp groups 0-5 | wait S(j+1)+LDTM issue | exp 6-7, max next, pack | st+arrive | total | start")
-    for j in range(min(nb, 32)):
-        s = tr[r][j]
-        print(f"{j:3d} | {s[2]-s[1]:6d} {s[3]-s[2]:6d} {s[4]-s[3]:6d} {s[5]-s[4]:6d} | {s[5]-s[1]:6d} | {s[1]-t0:7d}")
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    run()
+for _ in range(5):
+    g.replay()
+torch.cuda.synchronize()
+lib = _lib.load()
+n_ctas, pieces = _lib.prefix_schedule([(1, Lp, 0)], B, H, allow_split=os.environ.get("HYDRAGEN_B200_PREFIX_SPLIT", "1") != "0")
+buf = (ctypes.c_longlong * (160 * 16))()
+lib.hg_debug_prefix_trace(buf, 160 * 16)
+rows = [[buf[c * 16 + s] for s in range(11)] for c in range(n_ctas)]
+t0 = min(r[0] for r in rows)
+names = ["entry", "set-up done", "dep-wait passed", "p1 first scores", "p1 loop done", "p1 epilogue done", "pN first scores", "pN loop done",
+         "pN epilogue done", "merge done", "CTA done"]
+print(f"B={B} L={Lp} H={H} split={os.environ.get('HYDRAGEN_B200_PREFIX_SPLIT', '1')}: {n_ctas} CTAs, {len(pieces)} pieces; us after the first CTA's entry: min / median / max over CTAs")
+for s, nm in enumerate(names):
+    vals = sorted((r[s] - t0) / 1e3 for r in rows if r[s] >= t0)
+    if vals:
+        print(f"  {nm:18s} {vals[0]:8.2f} {vals[len(vals) // 2]:8.2f} {vals[-1]:8.2f}   (n={len(vals)})")

@@ -240,37 +240,34 @@ def test_causal_prefill_full_size_property():
     assert (lse[:, hs].double().cpu() - rl).abs().max().item() < 5e-3
 
 
-_EXPERIMENTAL = os.environ.get("HYDRAGEN_B200_TEST_EXPERIMENTAL") == "1"
-
-
-@pytest.mark.parametrize("softmax", [
-    "split",
-    # 'simple' passed a hand-run parity check (profiles/r01s_*); 'alt' has not been run on hardware yet (written after
-    # the GPU budget of round 1 was spent): both are opt-in here until a GPU run has seen them pass inside pytest
-    pytest.param("simple", marks=pytest.mark.skipif(not _EXPERIMENTAL, reason="set HYDRAGEN_B200_TEST_EXPERIMENTAL=1")),
-    pytest.param("alt", marks=pytest.mark.skipif(not _EXPERIMENTAL, reason="set HYDRAGEN_B200_TEST_EXPERIMENTAL=1")),
-])
-def test_split_column_softmax_variant(softmax):
-    """The alternative softmax organisations of the prefix kernel (HYDRAGEN_B200_PREFIX_SOFTMAX=split | simple | alt; off
-    by default: DESIGN.md 4.1) stay correct: run in a subprocess because the switch is read once per process."""
+@pytest.mark.parametrize("split", ["1", "0"])
+@pytest.mark.parametrize("ctas", [None, "5", "37"])
+def test_persistent_schedule_variants(split, ctas, monkeypatch):
+    """The persistent prefix kernel gives the oracle's result whatever the schedule: units cut between CTAs and merged
+    through the workspace (stream-K, the default) or dealt whole (HYDRAGEN_B200_PREFIX_SPLIT=0), on the full grid or on
+    a grid of 5 / 37 CTAs (HYDRAGEN_B200_PREFIX_CTAS, read once per process -> subprocess): many pieces per CTA,
+    many units per CTA, hierarchies of 2-3 levels incl. ragged ones in ONE launch."""
     import subprocess
-    import sys
 
     code = (
         "import torch, sys; sys.path.insert(0, %r)\n"
         "from oracle import hydragen_oracle as O\n"
         "from hydragen_b200.attention import hydragen_attention\n"
-        "for sizes, hq, hkv, d, dt in [([[300], [17, 130], [3] * 24], 8, 4, 128, torch.bfloat16), ([[1000], [4] * 260], 4, 4, 64, torch.float16), ([[70, 200, 5], [2] * 12], 8, 1, 128, torch.bfloat16)]:\n"
+        "for sizes, hq, hkv, d, dt in [([[300], [17, 130], [3] * 24], 8, 4, 128, torch.bfloat16), ([[1000], [4] * 260], 4, 4, 64, torch.float16),\n"
+        "                              ([[70, 200, 5], [2] * 12], 8, 1, 128, torch.bfloat16), ([[2100], [1] * 300], 2, 2, 128, torch.bfloat16)]:\n"
         "    c = O.build_case(sizes, hq, hkv, d, dtype=dt, seed=4)\n"
         "    dev = lambda x: None if x is None else ([dev(t) for t in x] if isinstance(x, list) else (x.cuda() if isinstance(x, torch.Tensor) else x))\n"
-        "    out = hydragen_attention(**{k: dev(v) for k, v in c.items()})\n"
-        "    err = (out.double().cpu() - O.hydragen_attention(**c)).abs().max().item()\n"
-        "    assert err <= (1.6e-2 if dt == torch.bfloat16 else 2e-3), (sizes, err)\n"
-        "print('split ok')\n"
+        "    for rep in range(3):\n"
+        "        out = hydragen_attention(**{k: dev(v) for k, v in c.items()})\n"
+        "        err = (out.double().cpu() - O.hydragen_attention(**c)).abs().max().item()\n"
+        "        assert err <= (1.6e-2 if dt == torch.bfloat16 else 2e-3), (sizes, rep, err)\n"
+        "print('schedule ok')\n"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, HYDRAGEN_B200_PREFIX_SOFTMAX=softmax)
+    env = dict(os.environ, HYDRAGEN_B200_PREFIX_SPLIT=split)
+    if ctas is not None:
+        env["HYDRAGEN_B200_PREFIX_CTAS"] = ctas
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
-    assert r.returncode == 0 and "split ok" in r.stdout, r.stdout + r.stderr
+    assert r.returncode == 0 and "schedule ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_no_unique_keys_early_return():
@@ -458,37 +455,38 @@ def test_hydragen_attention_decode_matches_unfused(sizes):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("splits", [2, 3, 8])
-def test_prefix_split_kv_partials_merge_to_full(dtype, splits):
-    """Split-KV prefix launch (hg_prefix_attn_split_fwd): the merged partials == the unsplit result == oracle,
-    for uniform and ragged (varlen) groups, incl. splits that receive no keys (out 0, lse -inf)."""
+@pytest.mark.parametrize("qps", [40, 300])
+def test_prefix_stream_k_ragged_groups(dtype, qps):
+    """Few (group, tile, head) units with ragged (varlen) key lengths: the persistent kernel cuts the long groups into
+    pieces (merged in-kernel from fp32 partials), clips pieces past a short group's end, and a group WITHOUT keys gives
+    out 0 / lse -inf.  out and LSE == oracle."""
     from hydragen_b200 import _lib
-    from hydragen_b200.attention import combine_lse_cuda
+    from hydragen_b200.flash import flash_attention_varlen
 
-    g = torch.Generator().manual_seed(splits)
-    lens = [700, 65, 130, 1]  # ragged groups: the short ones leave later splits empty
-    n, qps, hq, hkv, d = len(lens), 40, 4, 2, 128
-    q = torch.randn(n * qps, 1, hq, d, generator=g).to(dtype)
+    g = torch.Generator().manual_seed(qps)
+    lens = [700, 65, 0, 130, 1]
+    n, hq, hkv, d = len(lens), 4, 2, 128
+    q = torch.randn(n * qps, hq, d, generator=g).to(dtype)
     k = torch.randn(sum(lens), hkv, d, generator=g).to(dtype)
     v = torch.randn(sum(lens), hkv, d, generator=g).to(dtype)
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
-    qd, kd, vd, cud = q.cuda(), k.cuda(), v.cuda(), cu.cuda()
-    out = torch.empty(splits, n * qps, 1, hq, d, device="cuda", dtype=dtype)
-    lse = torch.empty(splits, n * qps, 1, hq, device="cuda", dtype=torch.float32)
-    _lib.prefix_attn_fwd(qd, kd, vd, out, lse, n, qps, kd.shape[0], 0, cud, max(lens), hq, hkv, d, hq * d, hkv * d, d**-0.5, kv_splits=splits)
-    merged, mlse = combine_lse_cuda([out[i] for i in range(splits)], [lse[i] for i in range(splits)], return_lse=True)
-    torch.cuda.synchronize()
-    assert torch.isinf(lse).any() or splits == 2  # some (group, split) pairs are empty
     cu_q = torch.arange(0, n + 1, dtype=torch.int32) * qps
-    ro, rl = O.flash_attention_varlen(q.view(n * qps, hq, d), k, v, cu_q, cu, qps, max(lens))
-    _assert_close(merged.view(n * qps, hq, d), ro, dtype, f"split-KV x{splits}")
-    rl = rl.permute(0, 2, 1).reshape(n * qps, hq)  # [n, h, qps] -> rows
-    assert (mlse.view(n * qps, hq).double().cpu() - rl).abs().max().item() < 5e-3
+    n_ctas, pieces = _lib.prefix_schedule([(n, 0, max(lens))], n * qps, hq)
+    assert any(p[8] for p in pieces), "this shape is meant to be split"
+    out, lse = flash_attention_varlen(q.cuda(), k.cuda(), v.cuda(), cu_q.cuda(), cu.cuda(), qps, max(lens))
+    torch.cuda.synchronize()
+    ro, rl = O.flash_attention_varlen(q, k, v, cu_q, cu, qps, max(lens))
+    empty = slice(2 * qps, 3 * qps)
+    assert (out[empty] == 0).all() and torch.isinf(lse[2]).all() and (lse[2] < 0).all()
+    _assert_close(out, ro, dtype, "stream-K ragged")
+    fin = torch.isfinite(rl)
+    assert (torch.isfinite(lse.cpu()) == fin).all()
+    assert (lse.double().cpu()[fin] - rl[fin]).abs().max().item() < 5e-3
 
 
-def test_operator_uses_split_kv_when_few_heads():
-    """A head-parallel rank's shape (few local heads, long prefix): the operator picks kv_splits > 1 by itself and
-    the result still matches the oracle."""
+def test_operator_few_heads_is_split_and_matches():
+    """A head-parallel rank's shape (few local heads, long prefix): the schedule cuts every unit into several pieces and
+    the operator's result still matches the oracle."""
     from hydragen_b200 import _lib
     from hydragen_b200.attention import hydragen_attention_nopad
 
@@ -497,10 +495,11 @@ def test_operator_uses_split_kv_when_few_heads():
     mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16)
     q, k, v, sk, sv = mk(b, 1, hq, d), mk(b, lu, hkv, d), mk(b, lu, hkv, d), mk(1, ls, hkv, d), mk(1, ls, hkv, d)
     sl = torch.randint(1, lu + 1, (b,), generator=g)
-    assert _lib.prefix_suggest_splits(torch.device("cuda:0"), 1, b, hq, ls, 8) > 1
+    n_ctas, pieces = _lib.prefix_schedule([(1, ls, 0)], b, hq)
+    assert n_ctas > 2 and all(p[8] for p in pieces)
     out = hydragen_attention_nopad(q.cuda(), k.cuda(), v.cuda(), [sk.cuda()], [sv.cuda()], seq_len=sl.cuda())
     ref = O.hydragen_attention_nopad(q, k, v, [sk], [sv], seq_len=sl)
-    _assert_close(out, ref, torch.bfloat16, "auto split-KV")
+    _assert_close(out, ref, torch.bfloat16, "stream-K, few heads")
 
 
 def test_host_decode_pipeline_matches_direct_calls():
