@@ -48,8 +48,14 @@ SYMBOLS = {
     "hg_prefix_attn_fwd": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
-         c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_void_p, c_int64, c_void_p],
+         c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_void_p],
     ),
+    "hg_prefix_attn_split_fwd": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
+         c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_int, c_void_p],
+    ),
+    "hg_prefix_suggest_splits": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "hg_prefix_attn_grouped_fwd": (
         c_int,
         [c_void_p, c_int64, c_int64, POINTER(PrefixLevel), c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_int64, c_void_p],
@@ -207,16 +213,21 @@ def rowwise_attn_fwd(q, k, v, seq_lens, cu_seqlens_k, kv_group_size, causal, out
 
 
 def prefix_attn_fwd(q, k, v, out, lse, n_groups, q_per_group, n_k_rows, k_len, cu_seqlens_k, max_k_len,
-                    hq, hkv, d, q_stride_row, kv_stride_row, sm_scale, workspace: Optional[torch.Tensor] = None, split: bool = True) -> None:
-    """One shared level.  ``split=False`` keeps every (group, tile, head) unit on one CTA (no workspace)."""
+                    hq, hkv, d, q_stride_row, kv_stride_row, sm_scale, kv_splits: int = 1) -> None:
+    """One shared level on the one-CTA-per-unit kernel.  out / lse hold kv_splits partial results back to back
+    ([kv_splits, rows, hq, d] / [kv_splits, rows, hq])."""
     ensure_init(q.device)
-    ws = (workspace if workspace is not None else prefix_workspace(q.device)) if split else None
     with torch.cuda.device(q.device):
-        rc = load().hg_prefix_attn_fwd(
+        rc = load().hg_prefix_attn_split_fwd(
             _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), n_groups, q_per_group, n_k_rows, k_len,
             _ptr(cu_seqlens_k), max_k_len, hq, hkv, d, q_stride_row, kv_stride_row, float(sm_scale),
-            dtype_code(q.dtype), _ptr(ws), 0 if ws is None else ws.numel(), _stream(q))
+            dtype_code(q.dtype), kv_splits, _stream(q))
     _check(rc, "hg_prefix_attn_fwd")
+
+
+def prefix_suggest_splits(device, n_groups: int, q_per_group: int, hq: int, max_k_len: int, max_splits: int) -> int:
+    ensure_init(device)
+    return int(load().hg_prefix_suggest_splits(n_groups, q_per_group, hq, max_k_len, max_splits))
 
 
 def make_prefix_level(k, v, out, lse, cu_seqlens_k, n_k_rows, kv_stride_row, n_groups, k_len, max_k_len) -> PrefixLevel:
@@ -236,9 +247,10 @@ def prefix_attn_grouped_fwd(q, n_q_rows, q_stride_row, levels: Sequence[PrefixLe
     _check(rc, "hg_prefix_attn_grouped_fwd")
 
 
-def prefix_schedule(levels, n_q_rows: int, hq: int, n_sms: int = 148, allow_split: bool = True):
+def prefix_schedule(levels, n_q_rows: int, hq: int, n_sms: int = 148, allow_split=True):
     """Host-side work schedule (no GPU needed).  ``levels``: list of (n_groups, k_len, max_k_len) with max_k_len > 0 for
-    ragged levels.  Returns (n_ctas, list of piece tuples (cta, unit, level, head, group, tile, b_lo, b_hi, split, slot))."""
+    ragged levels.  ``allow_split``: False / 0 whole units only, True / 1 what a launch does (stream-K where it pays),
+    2 always stream-K.  Returns (n_ctas, list of piece tuples (cta, unit, level, head, group, tile, b_lo, b_hi, split, slot))."""
     arr = (PrefixLevel * len(levels))()
     for a, (ng, kl, mk) in zip(arr, levels):
         a.n_groups, a.k_len, a.max_k_len = ng, kl, mk

@@ -2,8 +2,8 @@
 (same function names, argument meaning, return layouts and error behaviour), running on the
 hand-written sm_100a kernels behind the C ABI.
 
-Launches per call with L shared levels:  ONE persistent tcgen05 prefix launch over all L levels + 1 row-wise launch
-that does the suffix branch AND the (L+1)-way combine -- versus, in the reference, L flash-attn launches +
+Launches per call with L shared levels:  ONE tcgen05 prefix launch (L >= 2: the persistent kernel over all levels;
+L = 1: the one-CTA-per-unit kernel) + 1 row-wise launch that does the suffix branch AND the combine -- versus, in the reference, L flash-attn launches +
 L LSE transposes + cast + split-K + reduce + combine (Triton for 2 inputs, ~8 eager torch
 launches otherwise; hydragen/attention.py:246-352, hydragen/flash.py:163-281).
 """
@@ -17,6 +17,7 @@ from torch import Tensor
 
 from . import _lib
 from .flash import (
+    causal_attention_tc,
     decode_attention_fused,
     flash_attention,
     flash_attention_seqlen,
@@ -124,12 +125,15 @@ def hydragen_attention(
         n = scu.shape[0] - 1 if use_varlen else sk.shape[0]
         assert b % n == 0, f"{b} {n}"
         n_groups.append(n)
-    # every shared level in ONE persistent launch (the reference loops: one flash-attn call + LSE transpose per level)
+    # several shared levels: ONE persistent launch (the reference loops: one flash-attn call + LSE transpose per level);
+    # a single level with few work items (TP ranks): split-KV partials, merged by the combine below
+    early = k.shape[1] == 0 and len(shared_ks) == 1
     outs, lses = prefix_attention_levels(
         q, shared_ks, shared_vs, n_groups,
         [scu if uv else None for scu, uv in zip(shared_cu_seq_lens, use_varlens)],
-        [smax if uv else None for smax, uv in zip(shared_max_seq_lens, use_varlens)])
-    if k.shape[1] == 0 and len(shared_ks) == 1:
+        [smax if uv else None for smax, uv in zip(shared_max_seq_lens, use_varlens)],
+        max_partials=1 if early else _lib.HG_MAX_COMBINE - 1)
+    if early:
         return outs[0]  # attention.py:273-274, 330-331
 
     if k.shape[1] == 0:
@@ -137,7 +141,13 @@ def hydragen_attention(
         # sk = 0); here simply the merge of the shared levels.
         return combine_lse_cuda(outs, lses)
 
-    # suffix branch + (L+1)-way combine in one launch
+    if seq_lens is None:
+        # prefill of a chunk that attends to shared levels (hydragen/llama.py:513-521, 550-558): nq in the hundreds or
+        # thousands -- the causal suffix branch (attention.py:344) is dense work for the tensor cores, then one combine
+        res = causal_attention_tc(q, k, v)
+        if res is not None:
+            return combine_lse_cuda(outs + [res[0]], lses + [res[1]])
+    # decode / short chunks: suffix branch + (L+1)-way combine in one CUDA-core launch
     out, _ = suffix_attention_fused(q, k, v, seq_lens, causal=seq_lens is None, partial_outs=outs, partial_lses=lses)
     return out
 
@@ -177,7 +187,8 @@ def hydragen_attention_decode(
     outs, lses = prefix_attention_levels(
         q, shared_ks, shared_vs, n_groups,
         [scu if uv else None for scu, uv in zip(shared_cu_seq_lens, use_varlens)],
-        [smax if uv else None for smax, uv in zip(shared_max_seq_lens, use_varlens)])
+        [smax if uv else None for smax, uv in zip(shared_max_seq_lens, use_varlens)],
+        max_partials=_lib.HG_MAX_COMBINE)
     out, _ = decode_attention_fused(q, k_new, v_new, positions, k_cache, v_cache, outs, lses)
     return out
 

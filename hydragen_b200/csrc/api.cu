@@ -231,19 +231,45 @@ int hg_prefix_attn_grouped_fwd(const void* q, int64_t n_q_rows, int64_t q_stride
   return launch_prefix(p, dtype, (cudaStream_t)stream);
 }
 
-int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int n_groups, int q_per_group,
-                       int64_t n_k_rows, int k_len, const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
-                       int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype, void* workspace,
-                       int64_t workspace_bytes, void* stream) {
-  if (n_groups < 0 || q_per_group < 0) return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: bad sizes n_groups=%d q_per_group=%d", n_groups, q_per_group);
+int hg_prefix_attn_split_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int n_groups, int q_per_group,
+                             int64_t n_k_rows, int k_len, const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
+                             int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype, int kv_splits, void* stream) {
+  if (kv_splits < 1 || kv_splits > HG_MAX_COMBINE)
+    return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: kv_splits = %d outside [1, %d]", kv_splits, HG_MAX_COMBINE);
+  if (!g_info.ready) return set_error(HG_ERR_NOT_INITIALIZED, "prefix: hg_init() has not been called");
+  if (n_groups < 0 || q_per_group < 0 || n_k_rows < 0 || hq < 1 || hkv < 1)
+    return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: bad sizes n_groups=%d q_per_group=%d n_k_rows=%lld hq=%d hkv=%d", n_groups,
+                     q_per_group, (long long)n_k_rows, hq, hkv);
+  if (hq % hkv != 0) return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: hq (%d) must be a multiple of hkv (%d)", hq, hkv);
   if (n_groups == 0 || q_per_group == 0) return HG_OK;
+  if ((int64_t)n_groups * q_per_group * kv_splits > 0x7fffffffLL) return set_error(HG_ERR_UNSUPPORTED, "prefix: row counts must fit int32");
   hg_prefix_level lv;
   memset(&lv, 0, sizeof(lv));
   lv.k = k; lv.v = v; lv.out = out; lv.lse = lse; lv.cu_seqlens_k = cu_seqlens_k;
   lv.n_k_rows = n_k_rows; lv.kv_stride_row = kv_stride_row;
   lv.n_groups = n_groups; lv.k_len = k_len; lv.max_k_len = max_k_len;
-  return hg_prefix_attn_grouped_fwd(q, (int64_t)n_groups * q_per_group, q_stride_row, &lv, 1, hq, hkv, d, sm_scale, dtype, workspace,
-                                    workspace_bytes, stream);
+  PrefixParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.n_q_rows = (int64_t)n_groups * q_per_group; p.q_stride_row = q_stride_row;
+  p.hq = hq; p.hkv = hkv; p.d = d;
+  p.scale_log2 = sm_scale * kLog2e;
+  p.kv_splits = kv_splits;
+  if (q == nullptr) return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: null tensor pointer");
+  int rc = fill_prefix_levels(p, &lv, 1, "prefix");
+  if (rc != HG_OK) return rc;
+  return launch_prefix(p, dtype, (cudaStream_t)stream);
+}
+
+int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int n_groups, int q_per_group,
+                       int64_t n_k_rows, int k_len, const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
+                       int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype, void* stream) {
+  return hg_prefix_attn_split_fwd(q, k, v, out, lse, n_groups, q_per_group, n_k_rows, k_len, cu_seqlens_k, max_k_len, hq, hkv, d,
+                                  q_stride_row, kv_stride_row, sm_scale, dtype, 1, stream);
+}
+
+int hg_prefix_suggest_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits) {
+  if (n_groups < 1 || q_per_group < 1 || hq < 1 || max_k_len < 1 || max_splits < 1) return 1;
+  return suggest_prefix_splits(n_groups, q_per_group, hq, max_k_len, max_splits > HG_MAX_COMBINE ? HG_MAX_COMBINE : max_splits);
 }
 
 int hg_prefix_schedule(const hg_prefix_level* levels_host, int n_levels, int64_t n_q_rows, int hq, int n_sms, int allow_split,
@@ -263,7 +289,7 @@ int hg_prefix_schedule(const hg_prefix_level* levels_host, int n_levels, int64_t
     d.cu_seqlens_k = h.max_k_len > 0 ? reinterpret_cast<const int32_t*>(&d) : nullptr;  // non-null = "ragged level: cost from max_k_len"
   }
   SchedParams S;
-  int rc = build_prefix_schedule(p, n_sms, allow_split != 0, &S);
+  int rc = build_prefix_schedule(p, n_sms, allow_split < 0 ? 0 : (allow_split > 2 ? 2 : allow_split), &S);
   if (rc != HG_OK) return rc;
   if (n_ctas_out != nullptr) *n_ctas_out = S.n_ctas;
   int n = 0;

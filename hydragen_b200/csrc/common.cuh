@@ -184,11 +184,14 @@ struct PrefixParams {
   int causal;  // one level, bottom-right aligned causal mask inside every group (prefill): row r sees keys <= r + (k_len - q_per_group)
   void* workspace;  // stream-K partials and flags (hg_prefix_workspace_bytes); nullptr: whole units only
   int64_t workspace_bytes;
+  int kv_splits;    // one level only: >= 1; the level's out / lse then hold kv_splits partial results back to back
 };
 struct SchedParams;
 int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s);
-int build_prefix_schedule(const PrefixParams& p, int n_sms, bool allow_split, SchedParams* out);
+int build_prefix_schedule(const PrefixParams& p, int n_sms, int split_mode, SchedParams* out);  // split_mode: 0 whole units, 1 stream-K where it pays, 2 always stream-K
 int64_t prefix_workspace_bytes();
+int launch_prefix_unit(const PrefixParams& p, int kv_splits, int dtype, cudaStream_t s);  // prefix_unit_sm100.cu: one level, one CTA per unit
+int suggest_prefix_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits);
 
 int launch_allreduce_multimem(void* mc_ptr, void* out, const void* flags_dev, int rank, int world, int64_t nbytes, int dtype,
                               int n_blocks, cudaStream_t s);

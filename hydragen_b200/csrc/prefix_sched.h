@@ -26,6 +26,7 @@
 namespace hg {
 
 constexpr int kMaxLevels = 4;       // shared levels per launch
+constexpr int kMaxCtas = 160;       // persistent CTAs per launch (>= SMs of the device: 148)
 constexpr int kMaxUnitPieces = 24;  // pieces of one unit the merge handles (the host sizes the grid accordingly)
 
 struct SchedLevel {
@@ -36,16 +37,19 @@ struct SchedLevel {
   long long cost0;  // position of the level's first unit on the cost axis
 };
 
+struct UnitPos {
+  int unit, blk;
+};
+
 struct SchedParams {
   SchedLevel lv[kMaxLevels];
   int n_levels, hq, n_ctas, mode;
   int c0, min_piece, total_units;
   int heavy_first;  // unit order: row tiles descending first (the causal instantiation: later tiles see more keys)
   long long total_cost;
-};
-
-struct UnitPos {
-  int unit, blk;
+  // mode 0: the snapped cuts, tabulated by the host (sched_fill_bounds) -- the device never divides 64-bit numbers
+  // (r02f trace: computing them per CTA and per split piece cost microseconds of dependent divisions)
+  UnitPos bounds[kMaxCtas + 1];
 };
 HG_HD bool operator<(const UnitPos& a, const UnitPos& b) { return a.unit < b.unit || (a.unit == b.unit && a.blk < b.blk); }
 HG_HD bool operator==(const UnitPos& a, const UnitPos& b) { return a.unit == b.unit && a.blk == b.blk; }
@@ -65,7 +69,7 @@ HG_HD int sched_level_of_unit(const SchedParams& S, int unit) {
 }
 
 // Cut number j (0 .. n_ctas) of the cost axis, snapped: CTA j owns [boundary(j), boundary(j + 1)).
-HG_HD UnitPos sched_boundary(const SchedParams& S, int j) {
+inline UnitPos sched_boundary_compute(const SchedParams& S, int j) {
   if (j <= 0) return UnitPos{0, 0};
   if (j >= S.n_ctas) return UnitPos{S.total_units, 0};
   const long long x = (long long)j * S.total_cost / S.n_ctas;
@@ -83,6 +87,11 @@ HG_HD UnitPos sched_boundary(const SchedParams& S, int j) {
   }
   return UnitPos{L.unit0 + (int)uu, b};
 }
+
+inline void sched_fill_bounds(SchedParams& S) {
+  for (int j = 0; j <= S.n_ctas && j <= kMaxCtas; ++j) S.bounds[j] = sched_boundary_compute(S, j);
+}
+HG_HD UnitPos sched_boundary(const SchedParams& S, int j) { return S.bounds[j < 0 ? 0 : (j > S.n_ctas ? S.n_ctas : j)]; }
 
 HG_HD void sched_decode_unit(const SchedParams& S, int unit, SchedPiece& p) {
   const int l = sched_level_of_unit(S, unit);

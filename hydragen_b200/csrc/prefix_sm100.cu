@@ -39,10 +39,10 @@
 // All producer/consumer edges are mbarriers with phases counted across pieces (TMA complete_tx, tcgen05.commit,
 // thread arrives); there is no __syncthreads between set-up and teardown.
 //
-// Instantiations: <T, D, kCausal = false> the decode hot path (hg_prefix_attn_fwd / hg_prefix_attn_grouped_fwd);
-// <T, D, kCausal = true> prefill (hg_causal_attn_fwd, second translation unit prefix_sm100_causal.cu): bottom-right
-// aligned causal mask inside every group, whole units only, heavy row tiles first, only the visible key blocks are
-// streamed, masks only in the blocks crossing the diagonal.
+// Used for launches over SEVERAL shared levels (hg_prefix_attn_grouped_fwd with n_levels >= 2); one level goes to the
+// one-CTA-per-unit kernel of prefix_unit_sm100.cu, whose main loop measured 10-20 % faster per key block (launch_prefix
+// below).  The kCausal template parameter is kept in the code (the mask logic is shared) but only the unmasked form is
+// instantiated here.
 //
 // Algorithmic work per unit: 4 * rows * k_len * d FLOP.  Bound: tensor pipe (AI ~ 680 FLOP/B at the 7B config), with
 // the MUFU exp2 rate (16/clk/SM == the 128x128x128 MMA rate) the co-limiter.
@@ -55,6 +55,7 @@
 
 #include "common.cuh"
 #include "prefix_sched.h"
+#include "sm100_ptx.cuh"
 
 namespace hg {
 
@@ -70,7 +71,6 @@ __host__ __device__ constexpr uint32_t tmem_o(int t) { return 256u + (uint32_t)t
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 // ---- workspace (caller-owned, zero-initialised once; see hg_prefix_workspace_bytes) ----------------------
-constexpr int kMaxCtas = 160;             // >= SMs of the device (148)
 constexpr int kWsWordEpoch = 0;           // launches completed on this workspace
 constexpr int kWsWordExit = 1;            // CTAs of the running launch that are done
 constexpr int kWsWordFlags = 32;          // flag (cta, slot, tile) = word 32 + (cta * 2 + slot) * 2 + tile
@@ -82,212 +82,7 @@ __host__ __device__ constexpr int64_t ws_o_index(int d, int tile, int row, int c
 __host__ __device__ constexpr int64_t ws_ml_index(int d, int tile, int row) { return (int64_t)kTiles * BLOCK_M * d + (tile * BLOCK_M + row) * 2; }
 __host__ __device__ constexpr int64_t ws_bytes(int d) { return kWsFlagBytes + (int64_t)kMaxCtas * 2 * ws_slot_floats(d) * 4; }
 
-// ---- PTX wrappers ------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// One lane of the (converged) warp, known to the compiler as such: the uniform datapath can then
-// feed TMA / UMMA descriptors without a per-lane waterfall loop.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred P;\n"
-      "elect.sync _|P, 0xffffffff;\n"
-      "selp.b32 %0, 1, 0, P;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-
-// tcgen05.commit: the mbarrier gets one arrival when every MMA issued so far by this thread is done.
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem]; descriptors passed as (lo, hi) halves so that stepping the start
-// address along K is one 32-bit add per operand
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .b64 da, db;\n"
-      "setp.ne.b32 p, %6, 0;\n"
-      "mov.b64 da, {%1, %2};\n"
-      "mov.b64 db, {%3, %4};\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .b64 db;\n"
-      "setp.ne.b32 p, %5, 0;\n"
-      "mov.b64 db, {%2, %3};\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// Shared-memory matrix descriptor (sm_100 UMMA): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
-// version=1 [46,48) | layout [61,64) with SWIZZLE_128B = 2.  lo = start | LBO, hi = SBO | version | layout.
-__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
-  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
-}
-__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
-  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
-}
-
-// Instruction descriptor, kind::f16: D fmt [4,6) (1 = f32) | A fmt [7,10) | B fmt [10,13) (0 = f16, 1 = bf16) |
-// A major bit 15 | B major bit 16 (0 = K-major, 1 = MN-major) | N>>3 [17,23) | M>>4 [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int fmt, int b_mn_major, int m, int n) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);
-}
-
-#define HG_R32(a, o)                                                                                                    \
-  "=r"(a[o + 0]), "=r"(a[o + 1]), "=r"(a[o + 2]), "=r"(a[o + 3]), "=r"(a[o + 4]), "=r"(a[o + 5]), "=r"(a[o + 6]),        \
-      "=r"(a[o + 7]), "=r"(a[o + 8]), "=r"(a[o + 9]), "=r"(a[o + 10]), "=r"(a[o + 11]), "=r"(a[o + 12]), "=r"(a[o + 13]), \
-      "=r"(a[o + 14]), "=r"(a[o + 15]), "=r"(a[o + 16]), "=r"(a[o + 17]), "=r"(a[o + 18]), "=r"(a[o + 19]),               \
-      "=r"(a[o + 20]), "=r"(a[o + 21]), "=r"(a[o + 22]), "=r"(a[o + 23]), "=r"(a[o + 24]), "=r"(a[o + 25]),               \
-      "=r"(a[o + 26]), "=r"(a[o + 27]), "=r"(a[o + 28]), "=r"(a[o + 29]), "=r"(a[o + 30]), "=r"(a[o + 31])
-#define HG_W16(a, o)                                                                                                     \
-  "r"(a[o + 0]), "r"(a[o + 1]), "r"(a[o + 2]), "r"(a[o + 3]), "r"(a[o + 4]), "r"(a[o + 5]), "r"(a[o + 6]), "r"(a[o + 7]), \
-      "r"(a[o + 8]), "r"(a[o + 9]), "r"(a[o + 10]), "r"(a[o + 11]), "r"(a[o + 12]), "r"(a[o + 13]), "r"(a[o + 14]),       \
-      "r"(a[o + 15])
-#define HG_W32(a, o) HG_W16(a, o), HG_W16(a, o + 16)
-
-// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp gets lane (warp%4)*32 + t.
-#define HG_TMEM_LD32(taddr, a, o)                                                                               \
-  asm volatile(                                                                                                 \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                 \
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27," \
-      "%28,%29,%30,%31}, [%32];"                                                                                \
-      : HG_R32(a, o)                                                                                            \
-      : "r"(taddr))
-#define HG_TMEM_ST32(taddr, a, o)                                                                               \
-  asm volatile(                                                                                                 \
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "                                                          \
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27," \
-      "%28,%29,%30,%31};" ::HG_W32(a, o),                                                                       \
-      "r"(taddr)                                                                                                \
-      : "memory")
-#define HG_TMEM_ST16(taddr, a, o)                                                                          \
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::HG_W16(a, o), \
-               "r"(taddr)                                                                                  \
-               : "memory")
-
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-template <typename T>
-__device__ __forceinline__ uint32_t pack2(float a, float b);
-template <>
-__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));  // first source -> upper half
-  return r;
-}
-template <>
-__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  return r;
-}
-
-// ---- packed fp32x2 arithmetic (sm_100: one issue slot for two lanes' worth of FMA-pipe work) -------------
-__device__ __forceinline__ uint64_t pack_f2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack_f2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-// smem tile (generic-proxy writes fenced by the caller) -> global through the tensor map
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-template <int ID, int THREADS>
-__device__ __forceinline__ void named_bar_sync() {
-  asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(THREADS) : "memory");
-}
-
-__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// partials written by other SMs during this launch: read them at L2
-__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
-  float4 r;
-  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ float2 ld_cg_f2(const float* p) {
-  float2 r;
-  asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-  return r;
-}
-
-#if defined(HG_PREFIX_TRACE) && !defined(HG_PREFIX_TU_CAUSAL)
+#if defined(HG_PREFIX_TRACE)
 // Development aid (never in the shipped library): %globaltimer stamps [CTA][stage] of the most recent launch.
 // 0 entry | 1 set-up done | 2 griddepcontrol.wait passed | 3-5 first piece: first scores there, main loop done, epilogue
 // done | 6-8 the same for the last piece | 9 merge duties done | 10 CTA done   (3-9: row 0 of tile A's softmax warpgroup)
@@ -295,13 +90,24 @@ __device__ long long g_prefix_trace[kMaxCtas * 16];
 __device__ __forceinline__ void ptrace(int stage) {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  g_prefix_trace[blockIdx.x * 16 + stage] = t;
+  g_prefix_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + stage] = t;
 }
 #define HG_PTRACE(cond, stage) \
   do {                         \
     if (cond) ptrace(stage);   \
   } while (0)
+// cycles a designated thread spends inside one kind of barrier wait, accumulated over the launch
+#define HG_PWAIT(cond, slot, stmt)                                                        \
+  do {                                                                                    \
+    const long long hg_t0_ = clock64();                                                   \
+    stmt;                                                                                 \
+    if (cond) g_prefix_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] += clock64() - hg_t0_;             \
+  } while (0)
 #else
+#define HG_PWAIT(cond, slot, stmt) \
+  do {                             \
+    stmt;                          \
+  } while (0)
 #define HG_PTRACE(cond, stage) \
   do {                         \
   } while (0)
@@ -324,7 +130,9 @@ struct SmemLayout {
   static constexpr int kQ = 0;                              // 2 tiles (A, B)
   static constexpr int kKV = kQTileBytes * kTiles;
   static constexpr int kBars = kKV + kStageBytes * kStages;
-  static constexpr int kTotal = kBars + 512;
+  static constexpr int kSched = kBars + 512;  // copy of the launch's SchedParams (cut table included)
+  static constexpr int kCtx = kSched + ((int)sizeof(SchedParams) + 15) / 16 * 16;  // WarpCtx of the 8 softmax warps
+  static constexpr int kTotal = kCtx + 8 * 128;
 };
 
 struct Barriers {
@@ -337,6 +145,19 @@ struct Barriers {
   uint32_t pad_;
 };
 
+// Warp-uniform bookkeeping of a softmax warp, PARKED in shared memory while its main loop runs: the loop needs every
+// register (128 live scores + 32 packed P + the exp pipeline), and whatever is merely live ACROSS it gets spilled to local
+// memory and re-read per key block (r02l: 2.5 LDL per block, 1440-1800 cycles per block against round 1's uniform 1355).
+// What the loop needs travels in registers; what the epilogue needs is re-read from here after the loop.
+struct WarpCtx {
+  SchedIter it;
+  SchedPiece sp;
+  uint32_t c0, c1, g, np;  // uses of S buffer 0 / 1, key blocks, pieces this warp's tile has been through (barrier phases)
+  int duty[2];     // units cut into more than two pieces that this CTA holds a piece of (by workspace slot)
+  int first_piece;
+};
+static_assert(sizeof(WarpCtx) <= 128, "WarpCtx slot");
+
 struct LevelDev {
   void* out;           // [n_q_rows, hq, D]
   float* lse;          // [n_q_rows, hq] or nullptr
@@ -345,15 +166,21 @@ struct LevelDev {
   int pad_;
 };
 
+// Kernel parameters.  Order matters: what the main loop touches (scale, pointers) sits at the FRONT of the constant
+// bank; the 1.6 KB of tensor maps and the 1.4 KB schedule table come last.  (r02i/r02j: with the scale factor at byte
+// 4148 of the bank the compiler's per-block LDC of it missed the SM's constant cache and was served by the cache the
+// SMs of a GPC share -- whole GPCs ran their main loops up to 20 % slower than others, different ones every run.)
 struct alignas(64) PrefixKernelParams {
+  float scale_log2;
+  int hkv;
+  int pad0_;
+  int pad_;
+  uint32_t* ws_flags;  // workspace: epoch / exit counter / piece flags (nullptr: no unit is ever split)
+  float* ws_part;      // workspace: partial-result slots
+  LevelDev lv[kMaxLevels];
   CUtensorMap tmap_q;
   CUtensorMap tmap_k[kMaxLevels], tmap_v[kMaxLevels], tmap_o[kMaxLevels];
   SchedParams sched;
-  LevelDev lv[kMaxLevels];
-  int hkv;
-  float scale_log2;
-  uint32_t* ws_flags;  // workspace: epoch / exit counter / piece flags (nullptr: no unit is ever split)
-  float* ws_part;      // workspace: partial-result slots
 };
 
 // Everything a role needs to know about one piece (uniform over the CTA, recomputed by every role).
@@ -370,12 +197,12 @@ struct Piece {
 };
 
 template <bool kCausal>
-__device__ __forceinline__ void resolve_piece(const PrefixKernelParams& P, const SchedPiece& sp, Piece& pc) {
-  const SchedLevel& L = P.sched.lv[sp.level];
+__device__ __forceinline__ void resolve_piece(const PrefixKernelParams& P, const SchedParams& S, const SchedPiece& sp, Piece& pc) {
+  const SchedLevel& L = S.lv[sp.level];
   const LevelDev& V = P.lv[sp.level];
   pc.level = sp.level;
   pc.head = sp.head;
-  pc.kvh = sp.head / (P.sched.hq / P.hkv);
+  pc.kvh = sp.head / (S.hq / P.hkv);
   pc.mt = sp.mt;
   pc.q_row0 = sp.grp * L.q_per_group + sp.mt * (kTiles * BLOCK_M);
   pc.rows_left = L.q_per_group - sp.mt * (kTiles * BLOCK_M);
@@ -424,15 +251,17 @@ __device__ __noinline__ int split_role(const SchedParams& S, int unit, int cta, 
   return 0;
 }
 
-// Merge of a unit cut into 3+ pieces: this CTA's slice of the rows, one thread per row, 32 columns at a time.
+// Merge of a unit cut into 3+ pieces: this CTA's slice of the rows; one thread per (row, 32-column chunk), the
+// partials of two pieces in flight at a time (the loads are L2 round trips: latency, not bandwidth, is the cost).
 template <typename T, int D>
 __device__ __noinline__ void merge_duty(const SchedParams& S, const float* ws_part, const uint32_t* ws_flags, uint32_t epoch, int unit, int tid,
-                                        int lane, T* out, float* lse, int q_row0, int rows, int head, int hq) {
+                                        int lane, T* out, float* lse, int q_row0, int rows, int head, int hq, int cta) {
+  constexpr int kChunks = D / 32;
   int ctas[kMaxUnitPieces], slots[kMaxUnitPieces];
-  const int k = unit_pieces(S, unit, blockIdx.x, ctas, slots);
+  const int k = unit_pieces(S, unit, cta, ctas, slots);
   int me = 0;
   for (int p = 0; p < k; ++p)
-    if (ctas[p] == (int)blockIdx.x) me = p;
+    if (ctas[p] == cta) me = p;
   const int r_lo = (int)((long long)me * rows / k), r_hi = (int)((long long)(me + 1) * rows / k);
   const int ntile = rows > BLOCK_M ? 2 : 1;
   for (int i = lane; i < k * ntile; i += 32) {
@@ -441,49 +270,88 @@ __device__ __noinline__ void merge_duty(const SchedParams& S, const float* ws_pa
     }
   }
   __syncwarp();
-  for (int r = r_lo + tid; r < r_hi; r += kTiles * BLOCK_M) {
+  for (int item = tid; item < (r_hi - r_lo) * kChunks; item += kTiles * BLOCK_M) {
+    const int r = r_lo + item / kChunks, c0 = (item % kChunks) * 32;
     const int tt = r / BLOCK_M, rr = r % BLOCK_M;
+    // weights of the pieces for this row: 4 (max, sum) pairs in flight at a time
+    float w[kMaxUnitPieces];
     float mx = -INFINITY, lsum = 0.f;
-    for (int p = 0; p < k; ++p) {
-      const float2 ml = ld_cg_f2(ws_part + (int64_t)(ctas[p] * 2 + slots[p]) * ws_slot_floats(D) + ws_ml_index(D, tt, rr));
-      if (ml.y > 0.f) mx = fmaxf(mx, ml.x);
+    for (int p0 = 0; p0 < k; p0 += 4) {
+      float2 ml[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int p = min(p0 + i, k - 1);
+        ml[i] = ld_cg_f2(ws_part + (int64_t)(ctas[p] * 2 + slots[p]) * ws_slot_floats(D) + ws_ml_index(D, tt, rr));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (p0 + i < k) {
+          w[p0 + i] = ml[i].y > 0.f ? ml[i].x : -INFINITY;  // max for now
+          if (ml[i].y > 0.f) mx = fmaxf(mx, ml[i].x);
+        }
     }
-    for (int p = 0; p < k; ++p) {
-      const float2 ml = ld_cg_f2(ws_part + (int64_t)(ctas[p] * 2 + slots[p]) * ws_slot_floats(D) + ws_ml_index(D, tt, rr));
-      if (ml.y > 0.f) lsum += fast_exp2(ml.x - mx) * ml.y;
+    for (int p0 = 0; p0 < k; p0 += 4) {
+      float2 ml[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int p = min(p0 + i, k - 1);
+        ml[i] = ld_cg_f2(ws_part + (int64_t)(ctas[p] * 2 + slots[p]) * ws_slot_floats(D) + ws_ml_index(D, tt, rr));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (p0 + i < k) {
+          const float e = ml[i].y > 0.f ? fast_exp2(w[p0 + i] - mx) : 0.f;
+          w[p0 + i] = e;
+          lsum += e * ml[i].y;
+        }
     }
     const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
-    T* orow = out + ((int64_t)(q_row0 + r) * hq + head) * D;
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      float acc[32];
+    float acc[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-      for (int p = 0; p < k; ++p) {
-        const float* slot = ws_part + (int64_t)(ctas[p] * 2 + slots[p]) * ws_slot_floats(D);
-        const float2 ml = ld_cg_f2(slot + ws_ml_index(D, tt, rr));
-        if (ml.y > 0.f) {
-          const float w = fast_exp2(ml.x - mx) * inv;
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    for (int p = 0; p < k; p += 2) {
+      const float w0 = w[p] * inv, w1 = p + 1 < k ? w[p + 1] * inv : 0.f;
+      const float* s0 = ws_part + (int64_t)(ctas[p] * 2 + slots[p]) * ws_slot_floats(D);
+      const float* s1 = ws_part + (int64_t)(ctas[min(p + 1, k - 1)] * 2 + slots[min(p + 1, k - 1)]) * ws_slot_floats(D);
+      float4 a[8], b[8];
+      if (w0 != 0.f) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 o = ld_cg_f4(slot + ws_o_index(D, tt, rr, (c0 >> 2) + c));
-            acc[4 * c + 0] += w * o.x;
-            acc[4 * c + 1] += w * o.y;
-            acc[4 * c + 2] += w * o.z;
-            acc[4 * c + 3] += w * o.w;
-          }
+        for (int c = 0; c < 8; ++c) a[c] = ld_cg_f4(s0 + ws_o_index(D, tt, rr, (c0 >> 2) + c));
+      }
+      if (w1 != 0.f) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) b[c] = ld_cg_f4(s1 + ws_o_index(D, tt, rr, (c0 >> 2) + c));
+      }
+      if (w0 != 0.f) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          acc[4 * c + 0] += w0 * a[c].x;
+          acc[4 * c + 1] += w0 * a[c].y;
+          acc[4 * c + 2] += w0 * a[c].z;
+          acc[4 * c + 3] += w0 * a[c].w;
         }
       }
+      if (w1 != 0.f) {
 #pragma unroll
-      for (int c = 0; c < 32; c += 8) {
-        uint4 w;
-        w.x = pack2<T>(acc[c + 0], acc[c + 1]);
-        w.y = pack2<T>(acc[c + 2], acc[c + 3]);
-        w.z = pack2<T>(acc[c + 4], acc[c + 5]);
-        w.w = pack2<T>(acc[c + 6], acc[c + 7]);
-        st_v4(orow + c0 + c, w);
+        for (int c = 0; c < 8; ++c) {
+          acc[4 * c + 0] += w1 * b[c].x;
+          acc[4 * c + 1] += w1 * b[c].y;
+          acc[4 * c + 2] += w1 * b[c].z;
+          acc[4 * c + 3] += w1 * b[c].w;
+        }
       }
     }
-    if (lse != nullptr) lse[(int64_t)(q_row0 + r) * hq + head] = lsum > 0.f ? (mx + fast_log2(lsum)) * kLn2 : -INFINITY;
+    T* orow = out + ((int64_t)(q_row0 + r) * hq + head) * D + c0;
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+      uint4 wv;
+      wv.x = pack2<T>(acc[c + 0], acc[c + 1]);
+      wv.y = pack2<T>(acc[c + 2], acc[c + 3]);
+      wv.z = pack2<T>(acc[c + 4], acc[c + 5]);
+      wv.w = pack2<T>(acc[c + 6], acc[c + 7]);
+      st_v4(orow + c, wv);
+    }
+    if (c0 == 0 && lse != nullptr) lse[(int64_t)(q_row0 + r) * hq + head] = lsum > 0.f ? (mx + fast_log2(lsum)) * kLn2 : -INFINITY;
   }
 }
 
@@ -501,10 +369,30 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
   Barriers* bars = reinterpret_cast<Barriers*>(smem + L::kBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const SchedParams& S = P.sched;
-  const int hq = S.hq;
-  const float scale_log2 = P.scale_log2;
+  const int cta_id = blockIdx.y * gridDim.x + blockIdx.x;
+  // The schedule is read from shared memory: the out-of-line helpers take it by reference, and a reference into the
+  // kernel parameters is a generic pointer into constant memory -- every table look-up a dependent ~0.5 us load
+  // (r02g trace: 6 us per split-piece epilogue).  Copied once per CTA, before the set-up barrier.
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.sched);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + L::kSched);
+    for (int i = threadIdx.x; i < (int)(sizeof(SchedParams) / 4); i += kThreads) dst[i] = src[i];
+  }
+  const SchedParams& S = *reinterpret_cast<const SchedParams*>(smem + L::kSched);
+  const int hq = P.sched.hq;
+  float scale_log2 = P.scale_log2;
+  asm volatile("mov.b32 %0, %0;" : "+f"(scale_log2));  // opaque: stays in a register instead of being re-read from the constant bank
   HG_PTRACE(threadIdx.x == 0, 0);
+#if defined(HG_PREFIX_TRACE)
+  if (threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_prefix_trace[cta_id * 16 + 11] = smid;
+    g_prefix_trace[cta_id * 16 + 8] = 0;   // MMA warp A: cycles waiting for P (softmax late)
+    g_prefix_trace[cta_id * 16 + 14] = 0;  // softmax A, row 0: cycles waiting for S (tensor pipe late)
+    g_prefix_trace[cta_id * 16 + 15] = 0;  // MMA warp A: cycles waiting for K/V (TMA late)
+  }
+#endif
 
   // ---- one-time setup --------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -565,10 +453,10 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
       uint32_t nq[kTiles] = {0, 0};  // Q loads issued per tile
       SchedIter it;
       SchedPiece sp;
-      sched_begin(S, blockIdx.x, it);
+      sched_begin(S, cta_id, it);
       while (sched_next(S, it, sp)) {
         Piece pc;
-        resolve_piece<kCausal>(P, sp, pc);
+        resolve_piece<kCausal>(P, S, sp, pc);
         if (pc.n == 0) continue;
         const int n = pc.n;
         const int key0 = pc.k_row0 + pc.b_lo * BLOCK_N;
@@ -649,14 +537,14 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
       };
 
       uint32_t ri = 0;  // ring iterations consumed (all pieces, mirrors the producer)
-      uint32_t g = 0;   // key blocks of tile t issued so far: S buffer = g & 1, phases count in g
+      uint32_t cnt[2] = {0, 0};  // uses of S buffer 0 / 1 of tile t so far (barrier phases); block j of a piece uses buffer j & 1
       uint32_t np = 0;  // pieces in which tile t was active
       SchedIter it;
       SchedPiece sp;
-      sched_begin(S, blockIdx.x, it);
+      sched_begin(S, cta_id, it);
       while (sched_next(S, it, sp)) {
         Piece pc;
-        resolve_piece<kCausal>(P, sp, pc);
+        resolve_piece<kCausal>(P, S, sp, pc);
         if (pc.n == 0) continue;
         const int n = pc.n;
         const bool active = t == 0 || pc.rows_left > BLOCK_M;
@@ -669,7 +557,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
               if (u == -2) mbar_wait(&bars->q_full[t], np & 1);
               tc_fence_after();
               if (leader) {
-                const int sb = (g + u + 2) & 1;
+                const int sb = u + 2;  // block 0 -> buffer 0, block 1 -> buffer 1
                 issue_qk(st, sb);
                 umma_commit(&bars->s_full[t][sb]);
                 umma_commit(&bars->kv_empty[st]);
@@ -685,11 +573,10 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
         if (active) mbar_wait(&bars->o_empty[t], (np & 1) ^ 1);
         for (int j = 0; j < n; ++j) {
           const int st = ri % kStages;
-          mbar_wait(&bars->kv_full[st], (ri / kStages) & 1);
+          HG_PWAIT(t == 0 && lane == 0, 15, mbar_wait(&bars->kv_full[st], (ri / kStages) & 1));
           if (active) {
-            const uint32_t gj = g + j;
-            const int b = gj & 1;
-            mbar_wait(&bars->p_full[t][b], (gj >> 1) & 1);
+            const int b = j & 1;
+            HG_PWAIT(t == 0 && lane == 0, 8, mbar_wait(&bars->p_full[t][b], (cnt[b] + (uint32_t)(j >> 1)) & 1));
             tc_fence_after();
             if (leader) {
               issue_pv(st, b, j == 0);
@@ -708,7 +595,8 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
           ++ri;
         }
         if (active) {
-          g += n;
+          cnt[0] += (uint32_t)((n + 1) >> 1);
+          cnt[1] += (uint32_t)(n >> 1);
           ++np;
         }
       }
@@ -723,29 +611,50 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
     const uint32_t o_addr = tmem + lane_base + tmem_o(t);
     uint32_t* const ws_flags = P.ws_flags;
     const uint32_t epoch = ws_flags != nullptr ? *reinterpret_cast<volatile uint32_t*>(ws_flags + kWsWordEpoch) + 1u : 0u;
-    uint32_t g = 0, np = 0;  // as in the MMA warp of this tile
-    int duty_unit[2] = {-1, -1};  // units cut into more than two pieces that this CTA holds a piece of (by workspace slot)
-    bool first_piece = true;
-    SchedIter it;
-    SchedPiece sp;
-    sched_begin(S, blockIdx.x, it);
-    while (sched_next(S, it, sp)) {
+    volatile WarpCtx* const cx = reinterpret_cast<volatile WarpCtx*>(smem + L::kCtx + (warp - 4) * 128);
+    auto park_iter = [&](const SchedIter& it) {
+      cx->it.cur.unit = it.cur.unit; cx->it.cur.blk = it.cur.blk; cx->it.end.unit = it.end.unit; cx->it.end.blk = it.end.blk; cx->it.first = it.first;
+    };
+    {
+      SchedIter it0;
+      sched_begin(S, cta_id, it0);
+      if (lane == 0) {
+        park_iter(it0);
+        cx->c0 = 0; cx->c1 = 0; cx->g = 0; cx->np = 0; cx->duty[0] = -1; cx->duty[1] = -1; cx->first_piece = 1;
+      }
+      __syncwarp();
+    }
+    for (;;) {
+      SchedIter it;
+      it.cur.unit = cx->it.cur.unit; it.cur.blk = cx->it.cur.blk; it.end.unit = cx->it.end.unit; it.end.blk = cx->it.end.blk; it.first = cx->it.first;
+      SchedPiece sp;
+      if (!sched_next(S, it, sp)) break;
+      __syncwarp();
+      if (lane == 0) {
+        park_iter(it);
+        cx->sp.unit = sp.unit; cx->sp.level = sp.level; cx->sp.head = sp.head; cx->sp.grp = sp.grp; cx->sp.mt = sp.mt;
+        cx->sp.b_lo = sp.b_lo; cx->sp.b_hi = sp.b_hi; cx->sp.split = sp.split; cx->sp.slot = sp.slot;
+      }
+      __syncwarp();
       Piece pc;
-      resolve_piece<kCausal>(P, sp, pc);
+      resolve_piece<kCausal>(P, S, sp, pc);
       const int rows_valid = min(BLOCK_M, pc.rows_left - t * BLOCK_M);
       if (rows_valid <= 0) {  // tile B of a unit with at most 128 rows: nothing to compute, but the merge duty is shared
         if (pc.split) {
           int other;
-          if (split_role(S, pc.unit, blockIdx.x, &other) == 2) duty_unit[pc.slot] = pc.unit;
+          if (split_role(S, pc.unit, cta_id, &other) == 2 && lane == 0) cx->duty[pc.slot] = pc.unit;
         }
         continue;
       }
       const int n = pc.n;
-      const int k_len = pc.k_len;
       float m_used = -INFINITY;  // raw-score max the exponentials are referenced to
       float l = 0.f;
 
       if (n > 0) {
+        // block j of the piece uses S buffer j & 1; phases: one per use of a buffer (ph[b] = uses so far), one per key block
+        // for pv_done (gpar), one per piece for o_full
+        const uint32_t ph0 = cx->c0 & 1, ph1 = cx->c1 & 1, gpar = cx->g & 1;
+        const uint32_t o_parity = cx->np & 1;
         // Software pipeline over key blocks.  Per block the warp issues 64 MUFU exp2; everything else it has to do --
         // the scale FFMAs, the row sums and the 16-bit packing of block j, and (once S_t(j+1) can have landed: its
         // Q K^T is only issued after P_t(j-1) was consumed) fetching the scores of block j+1 from TMEM and reducing
@@ -753,16 +662,22 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
         // in-order warp always has independent work behind them.  Two score register arrays alternate between
         // "being exponentiated" and "being fetched".
         // row_end: first key (group-relative) this thread's row may NOT see; tile_end: the same for the tile's first row
-        const int row_end = kCausal ? pc.mt * (kTiles * BLOCK_M) + t * BLOCK_M + row + pc.causal_off + 1 : 0x7fffffff;
-        const int tile_end = kCausal ? pc.mt * (kTiles * BLOCK_M) + t * BLOCK_M + pc.causal_off + 1 : 0x7fffffff;
-        const bool ragged = (k_len % BLOCK_N) != 0;
-        const int b_lo = pc.b_lo, nb_group = pc.nb_group;
-        // block jl of the piece (group block b_lo + jl) holds a key some row of this tile must not see (warp-uniform)
-        auto needs_mask = [&](int jl) { return (ragged && b_lo + jl + 1 == nb_group) || (b_lo + jl + 1) * BLOCK_N > tile_end; };
+        // Masks: block jl of the piece (group block b_lo + jl) holds a key some row of this tile must not see from
+        // jl = first_mask on (the ragged last block of the group; causal: every block from the tile's diagonal on);
+        // this thread's row then sees the first rem0 - 64 * jl keys of the block.
+        int first_mask, rem0;
+        {
+          const int row_end = kCausal ? pc.mt * (kTiles * BLOCK_M) + t * BLOCK_M + row + pc.causal_off + 1 : 0x7fffffff;
+          const int tile_end = kCausal ? pc.mt * (kTiles * BLOCK_M) + t * BLOCK_M + pc.causal_off + 1 : 0x7fffffff;
+          const int ragged_at = (pc.k_len % BLOCK_N) != 0 ? pc.nb_group - 1 - pc.b_lo : 0x7fffffff;
+          first_mask = min(ragged_at, kCausal ? tile_end / BLOCK_N - pc.b_lo : 0x7fffffff);
+          rem0 = min(pc.k_len, row_end) - pc.b_lo * BLOCK_N;
+        }
+        auto needs_mask = [&](int jl) { return jl >= first_mask; };
         uint32_t sa[BLOCK_N], sb[BLOCK_N];
         float m_blk;
         auto mask_tail = [&](uint32_t(&x)[BLOCK_N], int jl) {
-          const int rem = min(k_len, row_end) - (b_lo + jl) * BLOCK_N;
+          const int rem = rem0 - jl * BLOCK_N;
 #pragma unroll
           for (int c = 0; c < BLOCK_N; ++c)
             if (c >= rem) x[c] = 0xff800000u;  // -inf
@@ -775,12 +690,13 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
         };
 
         // cur: scores of block j (masked, max known in m_blk); nxt: receives block j+1.
-        // kHasNext: block j+1 exists; kMaskNext: it needs a mask.
-        auto body = [&](int j, uint32_t(&cur)[BLOCK_N], uint32_t(&nxt)[BLOCK_N], auto has_next_tag, auto mask_next_tag) {
+        // kHasNext: block j+1 exists; kMaskNext: it needs a mask.  (Compile-time: as warp-uniform run-time flags -- two
+        // copies of the body instead of six -- every block took ~100 cycles longer, r02k.)
+        auto body = [&](int j, uint32_t(&cur)[BLOCK_N], uint32_t(&nxt)[BLOCK_N], auto has_next_tag, auto mask_next_tag, auto buf_tag) {
           constexpr bool kHasNext = decltype(has_next_tag)::value;
           constexpr bool kMaskNext = decltype(mask_next_tag)::value;
-          const uint32_t gj = g + j;
-          const uint32_t p_addr = tmem + lane_base + tmem_s(t, gj & 1);
+          constexpr int kB = decltype(buf_tag)::value;  // == j & 1: S buffer of this block
+          const uint32_t p_addr = tmem + lane_base + tmem_s(t, kB);
           const float m_new = fmaxf(m_used, m_blk);
           if (j == 0) {
             m_used = m_new;
@@ -789,7 +705,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
             if (__any_sync(0xffffffffu, need)) {
               // rare: O_t must be complete up to P_t(j-1) V_{j-1} before it is rescaled in place; P_t(j)
               // has not been released yet, so no later MMA can be touching O_t.
-              mbar_wait(&bars->pv_done[t], (gj - 1) & 1);
+              mbar_wait(&bars->pv_done[t], gpar ^ 1u ^ (uint32_t)kB);  // block j - 1 of the piece
               tc_fence_after();
               const float alpha = need ? fast_exp2((m_used - m_new) * scale_log2) : 1.f;
               if (need) {
@@ -835,9 +751,9 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
           }
           HG_TMEM_ST16(p_addr, pk, 0);  // keys 0..31 of P
           if constexpr (kHasNext) {     // S_t(j+1) has had ~3/4 of this block's MUFU time to land
-            mbar_wait(&bars->s_full[t][(gj + 1) & 1], ((gj + 1) >> 1) & 1);
+            HG_PWAIT(t == 0 && row == 0, 14, mbar_wait(&bars->s_full[t][kB ^ 1], (((uint32_t)(j >> 1) + kB) & 1) ^ (kB ? ph0 : ph1)));
             tc_fence_after();
-            const uint32_t s_addr = tmem + lane_base + tmem_s(t, (gj + 1) & 1);
+            const uint32_t s_addr = tmem + lane_base + tmem_s(t, kB ^ 1);
             HG_TMEM_LD32(s_addr + 0, nxt, 0);
             HG_TMEM_LD32(s_addr + 32, nxt, 32);
           }
@@ -867,14 +783,17 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
           }
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&bars->p_full[t][gj & 1]);
+          mbar_arrive(&bars->p_full[t][kB]);
         };
 
         {  // prologue: scores and row max of the piece's first block
-          mbar_wait(&bars->s_full[t][g & 1], (g >> 1) & 1);
-          HG_PTRACE(t == 0 && row == 0, first_piece ? 3 : 6);
+          mbar_wait(&bars->s_full[t][0], ph0);
+          HG_PTRACE(t == 0 && row == 0, cx->first_piece ? 3 : 6);
+#if defined(HG_PREFIX_TRACE)
+          if (t == 0 && row == 0 && cx->first_piece) g_prefix_trace[cta_id * 16 + 12] = clock64();
+#endif
           tc_fence_after();
-          const uint32_t s_addr = tmem + lane_base + tmem_s(t, g & 1);
+          const uint32_t s_addr = tmem + lane_base + tmem_s(t, 0);
           HG_TMEM_LD32(s_addr + 0, sa, 0);
           HG_TMEM_LD32(s_addr + 32, sa, 32);
           tmem_wait_ld();
@@ -886,26 +805,39 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
         }
         for (int j = 0; j < n; ++j) {
           const bool last = j + 1 == n, mask_next = !last && needs_mask(j + 1);
+          using B0 = std::integral_constant<int, 0>;
+          using B1 = std::integral_constant<int, 1>;
           if ((j & 1) == 0) {
-            if (last) body(j, sa, sb, std::false_type{}, std::false_type{});
-            else if (mask_next) body(j, sa, sb, std::true_type{}, std::true_type{});
-            else body(j, sa, sb, std::true_type{}, std::false_type{});
+            if (last) body(j, sa, sb, std::false_type{}, std::false_type{}, B0{});
+            else if (mask_next) body(j, sa, sb, std::true_type{}, std::true_type{}, B0{});
+            else body(j, sa, sb, std::true_type{}, std::false_type{}, B0{});
           } else {
-            if (last) body(j, sb, sa, std::false_type{}, std::false_type{});
-            else if (mask_next) body(j, sb, sa, std::true_type{}, std::true_type{});
-            else body(j, sb, sa, std::true_type{}, std::false_type{});
+            if (last) body(j, sb, sa, std::false_type{}, std::false_type{}, B1{});
+            else if (mask_next) body(j, sb, sa, std::true_type{}, std::true_type{}, B1{});
+            else body(j, sb, sa, std::true_type{}, std::false_type{}, B1{});
           }
         }
-        mbar_wait(&bars->o_full[t], np & 1);
+        mbar_wait(&bars->o_full[t], o_parity);
         tc_fence_after();
       }
 
-      // ---- epilogue of the piece -----------------------------------------------------------------
+      // ---- epilogue of the piece: everything about it is re-derived from the parked copy ---------------------
+      SchedPiece sq;
+      sq.unit = cx->sp.unit; sq.level = cx->sp.level; sq.head = cx->sp.head; sq.grp = cx->sp.grp; sq.mt = cx->sp.mt;
+      sq.b_lo = cx->sp.b_lo; sq.b_hi = cx->sp.b_hi; sq.split = cx->sp.split; sq.slot = cx->sp.slot;
+      Piece pe;
+      resolve_piece<kCausal>(P, S, sq, pe);
+      const int n_e = pe.n;
+      const int rows_e = min(BLOCK_M, pe.rows_left - t * BLOCK_M);
+      const bool first_piece = cx->first_piece != 0;
       HG_PTRACE(t == 0 && row == 0, first_piece ? 4 : 7);
-      const int tile_row0 = pc.q_row0 + t * BLOCK_M;
-      T* const out = reinterpret_cast<T*>(P.lv[pc.level].out);
-      float* const lse = P.lv[pc.level].lse;
-      float m_log2 = n > 0 ? m_used * scale_log2 : -INFINITY;  // reference max of this piece's exponentials, log2 units
+#if defined(HG_PREFIX_TRACE)
+      if (t == 0 && row == 0 && first_piece) g_prefix_trace[cta_id * 16 + 13] = clock64();
+#endif
+      const int tile_row0 = pe.q_row0 + t * BLOCK_M;
+      T* const out = reinterpret_cast<T*>(P.lv[pe.level].out);
+      float* const lse = P.lv[pe.level].lse;
+      float m_log2 = n_e > 0 ? m_used * scale_log2 : -INFINITY;  // reference max of this piece's exponentials, log2 units
       // A split unit: which CTAs hold its pieces, and which one am I?
       //   2 pieces (the common case: a cut of the stream-K schedule falls inside the unit): the CTA of the HEAD piece
       //     -- its last piece -- owns the unit: it folds the tail piece's partial (written long ago: a tail piece is
@@ -913,9 +845,9 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
       //   more pieces (few units on many SMs: the head-parallel ranks of a TP run): every piece leaves a partial and
       //     the pieces' CTAs merge the unit together after their main work, each a slice of the rows (below).
       bool to_workspace = false;
-      if (pc.split) {
+      if (pe.split) {
         int other = 0;
-        const int role = split_role(S, pc.unit, blockIdx.x, &other);
+        const int role = split_role(S, pe.unit, cta_id, &other);
         if (role == 1) {
           const uint32_t* flag = ws_flags + kWsWordFlags + other * 2 + t;
           while ((int32_t)(ld_acquire_gpu(flag) - epoch) < 0) {
@@ -923,7 +855,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
           const float* slot = P.ws_part + (int64_t)other * ws_slot_floats(D);
           const float2 ml = ld_cg_f2(slot + ws_ml_index(D, t, row));
           if (__any_sync(0xffffffffu, ml.y > 0.f)) {
-            // O_t <- w_own * O_t + w_part * partial, in place in TMEM (n > 0 here: the head piece of a unit whose tail
+            // O_t <- w_own * O_t + w_part * partial, in place in TMEM (n_e > 0 here: the head piece of a unit whose tail
             // holds keys holds keys itself); the normal epilogue below then finishes the unit
             const float m_all = fmaxf(m_log2, ml.y > 0.f ? ml.x : -INFINITY);
             const float w_own = fast_exp2(m_log2 - m_all), w_part = ml.y > 0.f ? fast_exp2(ml.x - m_all) : 0.f;
@@ -959,14 +891,14 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
           }
         } else {
           to_workspace = true;
-          if (role == 2) duty_unit[pc.slot] = pc.unit;
+          if (role == 2 && lane == 0) cx->duty[pe.slot] = pe.unit;
         }
       }
       if (to_workspace) {
         // Partial result -> workspace slot of this CTA: unnormalised O row (fp32), then (max in log2 units, row sum).
         // An empty piece leaves sum = 0 and is skipped by whoever merges.
-        float* slot = P.ws_part + (int64_t)(blockIdx.x * 2 + pc.slot) * ws_slot_floats(D);
-        if (n > 0) {
+        float* slot = P.ws_part + (int64_t)(cta_id * 2 + pe.slot) * ws_slot_floats(D);
+        if (n_e > 0) {
 #pragma unroll
           for (int c0 = 0; c0 < D; c0 += 32) {
             uint32_t o[32];
@@ -980,10 +912,10 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
           mbar_arrive(&bars->o_empty[t]);
           if (row == 0) mbar_arrive(&bars->q_empty[t]);  // every MMA of the piece is complete: Q_t is dead
         }
-        *reinterpret_cast<float2*>(slot + ws_ml_index(D, t, row)) = make_float2(m_log2, n > 0 ? l : 0.f);
+        *reinterpret_cast<float2*>(slot + ws_ml_index(D, t, row)) = make_float2(m_log2, n_e > 0 ? l : 0.f);
         __threadfence();
         if (t == 0) named_bar_sync<1, BLOCK_M>(); else named_bar_sync<2, BLOCK_M>();
-        if (row == 0) st_release_gpu(ws_flags + kWsWordFlags + (blockIdx.x * 2 + pc.slot) * 2 + t, epoch);
+        if (row == 0) st_release_gpu(ws_flags + kWsWordFlags + (cta_id * 2 + pe.slot) * 2 + t, epoch);
       } else {
         const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
         auto final8 = [&](const uint32_t(&o)[32], int c) {  // columns c .. c + 8 of the chunk -> normalised 16-bit
@@ -994,7 +926,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
           w.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
           return w;
         };
-        if (n > 0 && rows_valid == BLOCK_M) {
+        if (n_e > 0 && rows_e == BLOCK_M) {
           // full tile: rows -> the (dead) Q_t tile in the TMA 128-byte swizzle -> one bulk store per
           // 64-column half.  Row r keeps 16-byte chunk c at chunk slot c ^ (r & 7).
           uint8_t* stage = smem + L::kQ + t * L::kQTileBytes;
@@ -1016,15 +948,15 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
           if (t == 0) named_bar_sync<1, BLOCK_M>(); else named_bar_sync<2, BLOCK_M>();
           if (row == 0) {
 #pragma unroll
-            for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&P.tmap_o[pc.level], stage + h * L::kQHalfBytes, pc.head * D + h * 64, tile_row0);
+            for (int h = 0; h < L::kHalves; ++h) tma_store_2d(&P.tmap_o[pe.level], stage + h * L::kQHalfBytes, pe.head * D + h * 64, tile_row0);
             bulk_commit();
             bulk_wait_read();  // the staging tile has been read: the producer may load the next Q_t over it
             mbar_arrive(&bars->q_empty[t]);
           }
         } else {
-          const bool row_ok = row < rows_valid;
-          T* orow = out + ((int64_t)(tile_row0 + row) * hq + pc.head) * D;
-          if (n > 0) {
+          const bool row_ok = row < rows_e;
+          T* orow = out + ((int64_t)(tile_row0 + row) * hq + pe.head) * D;
+          if (n_e > 0) {
 #pragma unroll
             for (int c0 = 0; c0 < D; c0 += 32) {
               uint32_t o[32];
@@ -1043,15 +975,21 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
             for (int c = 0; c < D; c += 8) st_v4(orow + c, make_uint4(0, 0, 0, 0));
           }
         }
-        if (row < rows_valid && lse != nullptr)
-          lse[(int64_t)(tile_row0 + row) * hq + pc.head] = (l > 0.f) ? (m_log2 + fast_log2(l)) * kLn2 : -INFINITY;
+        if (row < rows_e && lse != nullptr)
+          lse[(int64_t)(tile_row0 + row) * hq + pe.head] = (l > 0.f) ? (m_log2 + fast_log2(l)) * kLn2 : -INFINITY;
       }
       HG_PTRACE(t == 0 && row == 0, first_piece ? 5 : 8);
-      first_piece = false;
-      if (n > 0) {
-        g += n;
-        ++np;
+      __syncwarp();
+      if (lane == 0) {
+        cx->first_piece = 0;
+        if (n_e > 0) {
+          cx->c0 = cx->c0 + (uint32_t)((n_e + 1) >> 1);
+          cx->c1 = cx->c1 + (uint32_t)(n_e >> 1);
+          cx->g = cx->g + (uint32_t)n_e;
+          cx->np = cx->np + 1u;
+        }
       }
+      __syncwarp();
     }
 
     // ---- merge duty (units cut into more than two pieces): this CTA's share of the rows -----------------------
@@ -1059,15 +997,15 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
     // the flags polled here are already up or about to be; nothing below depends on a CTA that is itself waiting)
     if (ws_flags != nullptr) {
       for (int dty = 0; dty < 2; ++dty) {
-        const int unit = duty_unit[dty];
-        if (unit < 0 || (dty == 1 && unit == duty_unit[0])) continue;
+        const int unit = cx->duty[dty];
+        if (unit < 0 || (dty == 1 && unit == cx->duty[0])) continue;
         SchedPiece su;
         sched_decode_unit(S, unit, su);
         su.b_lo = su.b_hi = su.split = su.slot = 0;
         Piece pu;
-        resolve_piece<kCausal>(P, su, pu);
+        resolve_piece<kCausal>(P, S, su, pu);
         merge_duty<T, D>(S, P.ws_part, ws_flags, epoch, unit, (warp - 4) * 32 + lane, lane, reinterpret_cast<T*>(P.lv[pu.level].out),
-                         P.lv[pu.level].lse, pu.q_row0, min(kTiles * BLOCK_M, pu.rows_left), pu.head, hq);
+                         P.lv[pu.level].lse, pu.q_row0, min(kTiles * BLOCK_M, pu.rows_left), pu.head, hq, cta_id);
       }
     }
     HG_PTRACE(t == 0 && row == 0, 9);
@@ -1088,7 +1026,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefix_attn_sm100_kernel(const __
     uint32_t* f = P.ws_flags;
     const uint32_t e = *reinterpret_cast<volatile uint32_t*>(f + kWsWordEpoch);
     __threadfence();
-    if (atomicAdd(f + kWsWordExit, 1u) == gridDim.x - 1) {
+    if (atomicAdd(f + kWsWordExit, 1u) == gridDim.x * gridDim.y - 1) {
       f[kWsWordExit] = 0u;
       __threadfence();
       f[kWsWordEpoch] = e + 1u;
@@ -1119,29 +1057,8 @@ static int make_tmap(CUtensorMap* map, const void* base, int dtype, uint64_t row
 }
 
 template <typename T, int D, bool kCausal>
-static int launch_prefix_inst(const PrefixParams& p, const SchedParams& sched, int dtype, cudaStream_t s) {
+static int launch_prefix_one(const PrefixKernelParams& kp, const SchedParams& sched, cudaStream_t s) {
   using L = SmemLayout<D>;
-  PrefixKernelParams kp;
-  memset(&kp, 0, sizeof(kp));
-  int rc;
-  if ((rc = make_tmap(&kp.tmap_q, p.q, dtype, (uint64_t)p.n_q_rows, (uint64_t)p.hq * D, (uint64_t)p.q_stride_row, BLOCK_M)) != HG_OK) return rc;
-  for (int l = 0; l < p.n_levels; ++l) {
-    const PrefixLevel& lv = p.levels[l];
-    if ((rc = make_tmap(&kp.tmap_k[l], lv.k, dtype, (uint64_t)lv.n_k_rows, (uint64_t)p.hkv * D, (uint64_t)lv.kv_stride_row, BLOCK_N)) != HG_OK) return rc;
-    if ((rc = make_tmap(&kp.tmap_v[l], lv.v, dtype, (uint64_t)lv.n_k_rows, (uint64_t)p.hkv * D, (uint64_t)lv.kv_stride_row, BLOCK_N)) != HG_OK) return rc;
-    if ((rc = make_tmap(&kp.tmap_o[l], lv.out, dtype, (uint64_t)p.n_q_rows, (uint64_t)p.hq * D, (uint64_t)p.hq * D, BLOCK_M)) != HG_OK) return rc;
-    kp.lv[l].out = lv.out;
-    kp.lv[l].lse = lv.lse;
-    kp.lv[l].cu = lv.cu_seqlens_k;
-    kp.lv[l].k_len = lv.k_len;
-  }
-  kp.sched = sched;
-  kp.hkv = p.hkv;
-  kp.scale_log2 = p.scale_log2;
-  if (sched.mode == 0) {
-    kp.ws_flags = reinterpret_cast<uint32_t*>(p.workspace);
-    kp.ws_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + kWsFlagBytes);
-  }
   const int smem_bytes = L::kTotal + 1024;
   static bool attr_set[64] = {};  // per instantiation and device; idempotent, racing threads set the same value
   const int dev = device_info().device;
@@ -1168,7 +1085,32 @@ static int launch_prefix_inst(const PrefixParams& p, const SchedParams& sched, i
   return check_launch("prefix_attn_sm100");
 }
 
-#if !defined(HG_PREFIX_TU_CAUSAL)
+template <typename T, int D, bool kCausal>
+static int launch_prefix_inst(const PrefixParams& p, const SchedParams& sched, int dtype, cudaStream_t s) {
+  using L = SmemLayout<D>;
+  PrefixKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  int rc;
+  if ((rc = make_tmap(&kp.tmap_q, p.q, dtype, (uint64_t)p.n_q_rows, (uint64_t)p.hq * D, (uint64_t)p.q_stride_row, BLOCK_M)) != HG_OK) return rc;
+  for (int l = 0; l < p.n_levels; ++l) {
+    const PrefixLevel& lv = p.levels[l];
+    if ((rc = make_tmap(&kp.tmap_k[l], lv.k, dtype, (uint64_t)lv.n_k_rows, (uint64_t)p.hkv * D, (uint64_t)lv.kv_stride_row, BLOCK_N)) != HG_OK) return rc;
+    if ((rc = make_tmap(&kp.tmap_v[l], lv.v, dtype, (uint64_t)lv.n_k_rows, (uint64_t)p.hkv * D, (uint64_t)lv.kv_stride_row, BLOCK_N)) != HG_OK) return rc;
+    if ((rc = make_tmap(&kp.tmap_o[l], lv.out, dtype, (uint64_t)p.n_q_rows, (uint64_t)p.hq * D, (uint64_t)p.hq * D, BLOCK_M)) != HG_OK) return rc;
+    kp.lv[l].out = lv.out;
+    kp.lv[l].lse = lv.lse;
+    kp.lv[l].cu = lv.cu_seqlens_k;
+    kp.lv[l].k_len = lv.k_len;
+  }
+  kp.sched = sched;
+  kp.hkv = p.hkv;
+  kp.scale_log2 = p.scale_log2;
+  if (sched.mode == 0) {
+    kp.ws_flags = reinterpret_cast<uint32_t*>(p.workspace);
+    kp.ws_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.workspace) + kWsFlagBytes);
+  }
+  return launch_prefix_one<T, D, kCausal>(kp, sched, s);
+}
 
 #ifdef HG_PREFIX_TRACE
 extern "C" int hg_debug_prefix_trace(long long* host_buf, int n) {
@@ -1188,9 +1130,19 @@ static int prefix_cta_cap() {
   return v;
 }
 
+// HYDRAGEN_B200_PREFIX_SPLIT_OVERHEAD (development knob, read once): cost of cutting units, in key blocks (default 6);
+// 0 = always stream-K, a huge value = never
+static long long prefix_split_overhead() {
+  static const long long v = [] {
+    const char* e = getenv("HYDRAGEN_B200_PREFIX_SPLIT_OVERHEAD");
+    return e != nullptr ? atoll(e) : 6ll;
+  }();
+  return v;
+}
+
 // The schedule of one launch: levels laid end to end on the cost axis, grid sized so that every CTA gets at least one
 // minimal piece and no unit is cut into more pieces than the merge handles.
-int build_prefix_schedule(const PrefixParams& p, int n_sms, bool allow_split, SchedParams* out) {
+int build_prefix_schedule(const PrefixParams& p, int n_sms, int split_mode, SchedParams* out) {
   SchedParams S;
   memset(&S, 0, sizeof(S));
   S.n_levels = p.n_levels;
@@ -1223,22 +1175,45 @@ int build_prefix_schedule(const PrefixParams& p, int n_sms, bool allow_split, Sc
   int cap = n_sms > 0 ? n_sms : 148;
   if (cap > kMaxCtas) cap = kMaxCtas;
   if (prefix_cta_cap() > 0 && prefix_cta_cap() < cap) cap = prefix_cta_cap();
-  if (allow_split) {
+  // Whole units dealt round-robin (mode 1) or stream-K (mode 0)?  Cutting units costs: a cut unit's tail piece writes
+  // its partial to the workspace, the head piece reads it back and both pay a pipeline ramp -- measured (r02g-r02i
+  // traces) at about 6 key blocks' worth of time on the CTA that finishes last.  Stream-K therefore only when the
+  // whole-unit makespan exceeds the stream-K share by more than that: few units on many SMs (long prefixes on the
+  // head-parallel ranks of a TP run, cfg#5) or a ragged last wave of many units; NOT the 128 units of cfg#2 on 148 SMs
+  // (32 vs 27.7 + 6 blocks).
+  bool split = false;
+  const int n_whole = std::max(1, std::min(cap, units));
+  if (split_mode == 2) split = true;
+  if (split_mode == 1) {
+    long long worst = 0;
+    for (int c = 0; c < n_whole; ++c) {
+      long long sum = 0;
+      for (int l = 0; l < p.n_levels; ++l) {
+        const SchedLevel& L = S.lv[l];
+        // units u of the level with u % n_whole == c
+        const long long first = ((c - L.unit0) % n_whole + n_whole) % n_whole;
+        if (first < L.n_units) sum += ((L.n_units - 1 - first) / n_whole + 1) * (long long)(L.nb_max + S.c0);
+      }
+      worst = std::max(worst, sum);
+    }
+    const long long g0 = std::min<long long>(cap, std::max<long long>(1, cost / (S.c0 + S.min_piece)));
+    split = worst > cost / g0 + prefix_split_overhead();
+  }
+  if (split) {
     S.mode = 0;
     long long g = cap;
     g = std::min<long long>(g, std::max<long long>(1, cost / (S.c0 + S.min_piece)));
     // pieces per unit <= w_max / (cost / g) + 2  must stay within kMaxUnitPieces
     g = std::min<long long>(g, std::max<long long>(1, (long long)(kMaxUnitPieces - 3) * cost / w_max));
     S.n_ctas = (int)std::max<long long>(1, g);
+    sched_fill_bounds(S);
   } else {
     S.mode = 1;
-    S.n_ctas = std::max(1, std::min(cap, units));
+    S.n_ctas = n_whole;
   }
   *out = S;
   return HG_OK;
 }
-
-int launch_prefix_causal(const PrefixParams& p, const SchedParams& sched, int dtype, cudaStream_t s);  // prefix_sm100_causal.cu
 
 int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
   if (p.n_levels < 1 || p.n_levels > kMaxLevels) return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: %d shared levels (1..%d)", p.n_levels, kMaxLevels);
@@ -1251,19 +1226,29 @@ int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
     if (lv.kv_stride_row % 8 != 0 || reinterpret_cast<uintptr_t>(lv.k) % 16 != 0 || reinterpret_cast<uintptr_t>(lv.v) % 16 != 0 ||
         reinterpret_cast<uintptr_t>(lv.out) % 16 != 0)
       return set_error(HG_ERR_UNSUPPORTED, "prefix: TMA needs 16-byte aligned bases and row strides");
+    if (lv.n_groups < 1 || p.n_q_rows % lv.n_groups != 0)
+      return set_error(HG_ERR_INVALID_ARGUMENT, "prefix: level %d: %d groups do not divide %lld query rows", l, lv.n_groups, (long long)p.n_q_rows);
   }
   if (p.d != 64 && p.d != 128) return set_error(HG_ERR_UNSUPPORTED, "prefix: head_dim %d not supported (64 or 128)", p.d);
+  const int kv_splits = p.kv_splits < 1 ? 1 : p.kv_splits;
   if (p.causal) {
     const PrefixLevel& lv = p.levels[0];
-    if (p.n_levels != 1 || lv.cu_seqlens_k != nullptr || lv.k_len < p.n_q_rows / lv.n_groups)
-      return set_error(HG_ERR_UNSUPPORTED, "prefix: the causal form takes one level of uniform groups with k_len >= q rows per group");
+    if (p.n_levels != 1 || lv.cu_seqlens_k != nullptr || kv_splits > 1 || lv.k_len < p.n_q_rows / lv.n_groups)
+      return set_error(HG_ERR_UNSUPPORTED, "prefix: the causal form takes one level of uniform groups with k_len >= q rows per group and no kv split");
   }
-  const bool allow_split = !p.causal && p.workspace != nullptr && p.workspace_bytes >= ws_bytes(p.d);
+  if (p.hq > 65535) return set_error(HG_ERR_UNSUPPORTED, "prefix: hq > 65535");
+  // ONE level: the one-CTA-per-unit kernel (prefix_unit_sm100.cu) -- per key block it is 10-20 % faster than the
+  // persistent one below (r02l-r02s), whose single launch only pays when it covers several shared levels.
+  // HYDRAGEN_B200_PREFIX_PERSISTENT=1 forces the persistent kernel (tests, measurements).
+  static const bool force_persistent = [] {
+    const char* e = getenv("HYDRAGEN_B200_PREFIX_PERSISTENT");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (p.causal || kv_splits > 1 || (p.n_levels == 1 && !force_persistent)) return launch_prefix_unit(p, kv_splits, dtype, s);
+  const int allow_split = (p.workspace != nullptr && p.workspace_bytes >= ws_bytes(p.d)) ? 1 : 0;
   SchedParams sched;
   int rc = build_prefix_schedule(p, device_info().sm_count, allow_split, &sched);
   if (rc != HG_OK) return rc;
-  sched.heavy_first = p.causal ? 1 : 0;
-  if (p.causal) return launch_prefix_causal(p, sched, dtype, s);
   if (dtype == HG_BF16) {
     if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, false>(p, sched, dtype, s);
     return launch_prefix_inst<__nv_bfloat16, 64, false>(p, sched, dtype, s);
@@ -1271,15 +1256,5 @@ int launch_prefix(const PrefixParams& p, int dtype, cudaStream_t s) {
   if (p.d == 128) return launch_prefix_inst<__half, 128, false>(p, sched, dtype, s);
   return launch_prefix_inst<__half, 64, false>(p, sched, dtype, s);
 }
-#else  // second translation unit: the causal instantiations (compiled in parallel)
-int launch_prefix_causal(const PrefixParams& p, const SchedParams& sched, int dtype, cudaStream_t s) {
-  if (dtype == HG_BF16) {
-    if (p.d == 128) return launch_prefix_inst<__nv_bfloat16, 128, true>(p, sched, dtype, s);
-    return launch_prefix_inst<__nv_bfloat16, 64, true>(p, sched, dtype, s);
-  }
-  if (p.d == 128) return launch_prefix_inst<__half, 128, true>(p, sched, dtype, s);
-  return launch_prefix_inst<__half, 64, true>(p, sched, dtype, s);
-}
-#endif
 
 }  // namespace hg

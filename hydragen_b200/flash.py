@@ -89,19 +89,87 @@ def prefix_attention_grouped(
     cu_seqlens_k: Optional[Tensor] = None,
     max_seqlen_k: Optional[int] = None,
 ) -> Tuple[Tensor, Tensor]:
-    """The prefix branch of ONE shared level: ``q [b, nq, hq, d]`` with the batch grouped contiguously by shared
-    parent (``b % n_groups == 0``), ``k, v`` either ``[n_groups, L, hkv, d]`` or, with ``cu_seqlens_k`` (int32
+    """The prefix branch of ONE shared level as one result: ``q [b, nq, hq, d]`` with the batch grouped contiguously by
+    shared parent (``b % n_groups == 0``), ``k, v`` either ``[n_groups, L, hkv, d]`` or, with ``cu_seqlens_k`` (int32
     ``[n_groups + 1]`` on device), packed ``[total, hkv, d]``.  Returns ``out [b, nq, hq, d]`` and ``lse [b, nq, hq]``
     (fp32) -- already in the layout the combine consumes (hydragen/attention.py:276-280, 333-338 need no transpose)."""
-    outs, lses = prefix_attention_levels(q, [k], [v], [n_groups], [cu_seqlens_k], [max_seqlen_k])
+    outs, lses = prefix_attention_partials(q, k, v, n_groups, cu_seqlens_k, max_seqlen_k, max_splits=1)
     return outs[0], lses[0]
 
 
+def _level_views(q, k, v, ng, cu, mx, hkv, d):
+    """(k, v, n_k_rows, k_len, kv_row_stride, max_k) of one shared level for the tensor-core kernels."""
+    if cu is not None:
+        if not (k.stride(2) == 1 and k.stride(1) == d and v.stride() == k.stride()):
+            k, v = k.contiguous(), v.contiguous()
+        return k, v, k.shape[0], 0, k.stride(0), (int(mx) if mx is not None else k.shape[0])
+    kv_rs = _rows_view(k)
+    if kv_rs is None or _rows_view(v) != kv_rs:
+        k, v = k.contiguous(), v.contiguous()
+        kv_rs = hkv * d
+    return k, v, k.shape[0] * k.shape[1], k.shape[1], kv_rs, k.shape[1]
+
+
+def _check_level(q, k, v, ng, cu, i=0):
+    b = q.shape[0]
+    if ng < 1 or b % ng != 0:
+        raise ValueError(f"batch {b} is not a multiple of the number of shared sequences {ng}")
+    if k.shape != v.shape or k.shape[-1] != q.shape[-1] or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise ValueError(f"shared K/V of level {i}: shapes {tuple(k.shape)} / {tuple(v.shape)}, dtypes {k.dtype} / {v.dtype}")
+    if cu is not None:
+        if k.ndim != 3:
+            raise ValueError("varlen shared K/V must be [total, kvheads, d]")
+        if cu.dtype != torch.int32 or cu.shape[0] != ng + 1:
+            raise ValueError("cu_seqlens_k must be int32 of n_groups + 1 entries")
+    elif k.ndim != 4 or k.shape[0] != ng:
+        raise ValueError(f"shared K/V must be [n_groups, L, kvheads, d], got {tuple(k.shape)}")
+
+
 def prefix_attention_partials(q, k, v, n_groups, cu_seqlens_k=None, max_seqlen_k=None, max_splits: int = 1):
-    """Round-1 name: the prefix branch as a LIST of partial results.  Split-KV now happens inside the persistent
-    kernel (stream-K pieces merged in the launch itself), so the list always holds one entry."""
-    out, lse = prefix_attention_grouped(q, k, v, n_groups, cu_seqlens_k, max_seqlen_k)
-    return [out], [lse]
+    """The prefix branch of ONE shared level as a list of partial results: when the launch has too few (group, tile,
+    head) work items to fill the GPU -- the head-parallel ranks of a tensor-parallel run -- the keys are cut into up to
+    ``max_splits`` ranges (split-KV) and one ``(out, lse)`` pair per range is returned, to be merged by the combine that
+    follows anyway.  Returns (list of out, list of lse)."""
+    b, nq, hq, d = q.shape
+    _check_level(q, k, v, n_groups, cu_seqlens_k)
+    hkv = k.shape[-2]
+    sm_scale = d**-0.5  # hydragen/flash.py:293
+    backend = _prefix_backend()
+    use_tc = q.dtype in _TC_DTYPES and d in _TC_HEAD_DIMS and backend != "rowwise"
+    if backend == "tcgen05" and not use_tc:
+        raise ValueError(f"tcgen05 prefix kernel does not take dtype {q.dtype} / head_dim {d}")
+    varlen = cu_seqlens_k is not None
+    splits = 1
+    if use_tc and max_splits > 1:
+        k_max = int(max_seqlen_k) if (varlen and max_seqlen_k is not None) else (k.shape[0] if varlen else k.shape[1])
+        splits = _lib.prefix_suggest_splits(q.device, n_groups, (b // n_groups) * nq, hq, k_max, max_splits)
+    out = torch.empty((splits, b, nq, hq, d), device=q.device, dtype=q.dtype)
+    lse = torch.empty((splits, b, nq, hq), device=q.device, dtype=torch.float32)
+    if use_tc:
+        q_rs = _rows_view(q)
+        if q_rs is None:
+            q = q.contiguous()
+            q_rs = hq * d
+        k, v, n_k_rows, k_len, kv_rs, max_k = _level_views(q, k, v, n_groups, cu_seqlens_k, max_seqlen_k, hkv, d)
+        _lib.prefix_attn_fwd(q, k, v, out, lse, n_groups, (b // n_groups) * nq, n_k_rows, k_len, cu_seqlens_k, max_k,
+                             hq, hkv, d, q_rs, kv_rs, sm_scale, kv_splits=splits)
+    else:
+        # CUDA-core path (fp32, other head dims): every sequence walks its parent's keys.
+        if not _inner_ok(q):
+            q = q.contiguous()
+        if not _inner_ok(k):
+            k = k.contiguous()
+        if not _inner_ok(v) or v.stride() != k.stride():
+            v = v.contiguous()
+            k = k.contiguous()
+        if varlen:
+            strides = (0, k.stride(0), k.stride(1))
+            lk = int(max_seqlen_k) if max_seqlen_k is not None else k.shape[0]
+        else:
+            strides = (k.stride(0), k.stride(1), k.stride(2))
+            lk = k.shape[1]
+        _lib.rowwise_attn_fwd(q, k, v, None, cu_seqlens_k, b // n_groups, False, out[0], lse[0], lk, strides, [], [], sm_scale)
+    return [out[i] for i in range(splits)], [lse[i] for i in range(splits)]
 
 
 def prefix_attention_levels(
@@ -111,80 +179,79 @@ def prefix_attention_levels(
     n_groups: Sequence[int],
     cu_seqlens: Sequence[Optional[Tensor]],
     max_seqlens: Sequence[Optional[int]],
+    max_partials: int = 1,
 ):
-    """The prefix branch of EVERY shared level of a hierarchy (the loop of hydragen/attention.py:250-341) in one
-    persistent tcgen05 launch: returns ``(outs, lses)``, one ``[b, nq, hq, d]`` / ``[b, nq, hq]`` pair per level.
-    fp32 inputs and head dims the tensor-core kernel does not take run level by level on the CUDA-core kernel."""
+    """The prefix branch of EVERY shared level of a hierarchy (the loop of hydragen/attention.py:250-341): returns
+    ``(outs, lses)`` lists of ``[b, nq, hq, d]`` / ``[b, nq, hq]`` partial results for the combine.
+
+    * two or more levels (16-bit, d in {64, 128}): ONE persistent tcgen05 launch over all of them
+      (hg_prefix_attn_grouped_fwd), one partial per level;
+    * one level: the one-CTA-per-unit tcgen05 kernel; with ``max_partials > 1`` and few work items (the ranks of a
+      tensor-parallel run) its keys are cut into up to that many ranges, one partial each;
+    * fp32 inputs and other head dims: level by level on the CUDA-core kernel."""
     b, nq, hq, d = q.shape
     n_levels = len(shared_ks)
     if not (len(shared_vs) == len(n_groups) == len(cu_seqlens) == len(max_seqlens) == n_levels):
         raise ValueError("one entry per shared level is needed in every list")
     if n_levels == 0:
         return [], []
-    sm_scale = d**-0.5  # hydragen/flash.py:293
     backend = _prefix_backend()
     use_tc = q.dtype in _TC_DTYPES and d in _TC_HEAD_DIMS and backend != "rowwise"
-    if backend == "tcgen05" and not use_tc:
-        raise ValueError(f"tcgen05 prefix kernel does not take dtype {q.dtype} / head_dim {d}")
+    if n_levels == 1 or not use_tc or os.environ.get("HYDRAGEN_B200_PREFIX_GROUPED", "1") == "0":
+        outs, lses = [], []
+        per_level = max(1, max_partials // n_levels)
+        for i in range(n_levels):
+            o, l = prefix_attention_partials(q, shared_ks[i], shared_vs[i], int(n_groups[i]), cu_seqlens[i], max_seqlens[i], max_splits=per_level)
+            outs += o
+            lses += l
+        return outs, lses
+    sm_scale = d**-0.5  # hydragen/flash.py:293
     hkv = shared_ks[0].shape[-2]
     outs = [torch.empty((b, nq, hq, d), device=q.device, dtype=q.dtype) for _ in range(n_levels)]
     lses = [torch.empty((b, nq, hq), device=q.device, dtype=torch.float32) for _ in range(n_levels)]
-    q_rs = None
-    if use_tc:
-        q_rs = _rows_view(q)
-        if q_rs is None:
-            q = q.contiguous()
-            q_rs = hq * d
-    elif not _inner_ok(q):
+    q_rs = _rows_view(q)
+    if q_rs is None:
         q = q.contiguous()
+        q_rs = hq * d
     descs, keep = [], []
     for i in range(n_levels):
         k, v, ng, cu, mx = shared_ks[i], shared_vs[i], int(n_groups[i]), cu_seqlens[i], max_seqlens[i]
-        if ng < 1 or b % ng != 0:
-            raise ValueError(f"batch {b} is not a multiple of the number of shared sequences {ng}")
-        if k.shape != v.shape or k.shape[-2] != hkv or k.shape[-1] != d or k.dtype != q.dtype or v.dtype != q.dtype:
-            raise ValueError(f"shared K/V of level {i}: shapes {tuple(k.shape)} / {tuple(v.shape)}, dtypes {k.dtype} / {v.dtype}")
-        varlen = cu is not None
-        if varlen:
-            if k.ndim != 3:
-                raise ValueError("varlen shared K/V must be [total, kvheads, d]")
-            if cu.dtype != torch.int32 or cu.shape[0] != ng + 1:
-                raise ValueError("cu_seqlens_k must be int32 of n_groups + 1 entries")
-        elif k.ndim != 4 or k.shape[0] != ng:
-            raise ValueError(f"shared K/V must be [n_groups, L, kvheads, d], got {tuple(k.shape)}")
-        if use_tc:
-            if varlen:
-                if not (k.stride(2) == 1 and k.stride(1) == d and v.stride() == k.stride()):
-                    k, v = k.contiguous(), v.contiguous()
-                n_k_rows, k_len, kv_rs = k.shape[0], 0, k.stride(0)
-                max_k = int(mx) if mx is not None else k.shape[0]
-            else:
-                kv_rs = _rows_view(k)
-                if kv_rs is None or _rows_view(v) != kv_rs:
-                    k, v = k.contiguous(), v.contiguous()
-                    kv_rs = hkv * d
-                n_k_rows, k_len = k.shape[0] * k.shape[1], k.shape[1]
-                max_k = 0
-            keep += [k, v]
-            descs.append(_lib.make_prefix_level(k, v, outs[i], lses[i], cu, n_k_rows, kv_rs, ng, k_len, max_k))
-        else:
-            # CUDA-core path (fp32, other head dims): every sequence walks its parent's keys.
-            if not _inner_ok(k):
-                k = k.contiguous()
-            if not _inner_ok(v) or v.stride() != k.stride():
-                v = v.contiguous()
-                k = k.contiguous()
-            if varlen:
-                strides = (0, k.stride(0), k.stride(1))
-                lk = int(mx) if mx is not None else k.shape[0]
-            else:
-                strides = (k.stride(0), k.stride(1), k.stride(2))
-                lk = k.shape[1]
-            _lib.rowwise_attn_fwd(q, k, v, None, cu, b // ng, False, outs[i], lses[i], lk, strides, [], [], sm_scale)
+        _check_level(q, k, v, ng, cu, i)
+        if k.shape[-2] != hkv:
+            raise ValueError("all shared levels must have the same number of kv heads")
+        k, v, n_k_rows, k_len, kv_rs, max_k = _level_views(q, k, v, ng, cu, mx, hkv, d)
+        keep += [k, v]
+        descs.append(_lib.make_prefix_level(k, v, outs[i], lses[i], cu, n_k_rows, kv_rs, ng, k_len, max_k if cu is not None else 0))
     # one launch covers up to MAX_PREFIX_LEVELS levels (deeper hierarchies: one launch per chunk of levels)
     for i in range(0, len(descs), _lib.MAX_PREFIX_LEVELS):
         _lib.prefix_attn_grouped_fwd(q, b * nq, q_rs, descs[i : i + _lib.MAX_PREFIX_LEVELS], hq, hkv, d, sm_scale, split=_prefix_split())
     return outs, lses
+
+
+def causal_attention_tc(q: Tensor, k: Tensor, v: Tensor) -> Optional[Tuple[Tensor, Tensor]]:
+    """Causal self-attention of a prefill chunk on the tcgen05 kernel when the shape allows it (16-bit, d in {64, 128},
+    sk >= sq, at least one key block of queries): ``(out [b, sq, hq, d], lse [b, sq, hq])``; None otherwise (the
+    caller then uses the CUDA-core kernel: fp32, other head dims, chunks too short to be worth a tensor-core launch)."""
+    b, sq, hq, d = q.shape
+    sk = k.shape[1]
+    backend = _causal_backend()
+    use_tc = q.dtype in _TC_DTYPES and d in _TC_HEAD_DIMS and sk >= sq and backend != "rowwise" and (backend == "tcgen05" or sq >= 64)
+    if backend == "tcgen05" and not use_tc:
+        raise ValueError(f"tcgen05 causal kernel does not take dtype {q.dtype} / head_dim {d} / sq {sq} > sk {sk}")
+    if not use_tc:
+        return None
+    q_rs = _rows_view(q)
+    if q_rs is None:
+        q = q.contiguous()
+        q_rs = hq * d
+    kv_rs = _rows_view(k)
+    if kv_rs is None or _rows_view(v) != kv_rs:
+        k, v = k.contiguous(), v.contiguous()
+        kv_rs = k.shape[2] * d
+    out = torch.empty((b, sq, hq, d), device=q.device, dtype=q.dtype)
+    lse = torch.empty((b, sq, hq), device=q.device, dtype=torch.float32)
+    _lib.causal_attn_fwd(q, k, v, out, lse, b, sq, sk, hq, k.shape[2], d, q_rs, kv_rs, d**-0.5)
+    return out, lse
 
 
 def flash_attention(q: Tensor, k: Tensor, v: Tensor, causal: bool = False) -> Tuple[Tensor, Tensor]:
@@ -195,29 +262,12 @@ def flash_attention(q: Tensor, k: Tensor, v: Tensor, causal: bool = False) -> Tu
     if not causal:
         out, lse = prefix_attention_grouped(q, k, v, n_groups=b)
         return out, lse.permute(0, 2, 1)
-    sk = k.shape[1]
-    backend = _causal_backend()
     # prefill chunks of at least one key block go to the tensor cores; shorter ones (launch-bound either way; the
-    # CUDA-core kernel keeps P in fp32) and shapes the tcgen05 kernel does not take (fp32, other head dims, sk < sq)
-    # stay on the CUDA-core kernel
-    use_tc = q.dtype in _TC_DTYPES and d in _TC_HEAD_DIMS and sk >= sq and backend != "rowwise" and (backend == "tcgen05" or sq >= 64)
-    if backend == "tcgen05" and not use_tc:
-        raise ValueError(f"tcgen05 causal kernel does not take dtype {q.dtype} / head_dim {d} / sq {sq} > sk {sk}")
-    if use_tc:
-        q_rs = _rows_view(q)
-        if q_rs is None:
-            q = q.contiguous()
-            q_rs = hq * d
-        kv_rs = _rows_view(k)
-        if kv_rs is None or _rows_view(v) != kv_rs:
-            k, v = k.contiguous(), v.contiguous()
-            kv_rs = k.shape[2] * d
-        out = torch.empty((b, sq, hq, d), device=q.device, dtype=q.dtype)
-        lse = torch.empty((b, sq, hq), device=q.device, dtype=torch.float32)
-        _lib.causal_attn_fwd(q, k, v, out, lse, b, sq, sk, hq, k.shape[2], d, q_rs, kv_rs, d**-0.5)
-        return out, lse.permute(0, 2, 1)
-    out, lse = _rowwise(q, k, v, None, causal=True)
-    return out, lse.permute(0, 2, 1)
+    # CUDA-core kernel keeps P in fp32) and shapes the tcgen05 kernel does not take stay on the CUDA-core kernel
+    res = causal_attention_tc(q, k, v)
+    if res is None:
+        res = _rowwise(q, k, v, None, causal=True)
+    return res[0], res[1].permute(0, 2, 1)
 
 
 def flash_attention_varlen(

@@ -8,6 +8,11 @@ and a decode step is that for every layer.  The three stages run on three stream
 events, so layer i+1's upload and layer i-1's download overlap layer i's kernels (PCIe is full duplex); a layer's
 staging buffers are only rewritten after the previous step's kernels of that layer have finished.  torch supplies
 streams, events and pinned memory; the kernels are the C-ABI library's.
+
+``capture()`` records one whole step -- every layer's copies and kernels on the three streams, with their
+dependencies -- into ONE CUDA graph (the host and staging buffers are static), so a step costs one graph launch
+instead of ~10 Python-issued stream operations per layer: the step is then bound by PCIe, not by launch overhead
+(round-1 review: the eager form scaled 2.5x from 1 to 8 GPUs where the 8 independent PCIe links allow ~8x).
 """
 
 from __future__ import annotations
@@ -78,6 +83,38 @@ class HostDecodePipeline:
                 self.d2h.wait_event(done)
                 ly.out_host.copy_(ly.out_dev, non_blocking=True)
                 ly.out_dev.record_stream(self.d2h)
+
+    def capture(self, layers: Sequence[HostDecodeLayer], positions: Tensor, after_layer=None) -> "torch.cuda.CUDAGraph":
+        """One decode step over ``layers`` as a CUDA graph: the upload / kernel / download streams fork from the
+        capturing stream and join it again, so replaying the graph on a stream orders whole steps on that stream.
+        Run ``step`` once eagerly beforehand (library set-up, workspace, collective arenas must exist)."""
+        graph = torch.cuda.CUDAGraph()
+        self.synchronize()
+        self._done = {}
+        with torch.cuda.graph(graph):
+            cap = torch.cuda.current_stream(self.device)
+            self.h2d.wait_stream(cap)
+            self.d2h.wait_stream(cap)
+            for i, ly in enumerate(layers):
+                with torch.cuda.stream(self.h2d):
+                    ly.q_dev.copy_(ly.q_host, non_blocking=True)
+                    ly.k_dev.copy_(ly.k_host, non_blocking=True)
+                    ly.v_dev.copy_(ly.v_host, non_blocking=True)
+                    up = torch.cuda.Event()
+                    up.record(self.h2d)
+                cap.wait_event(up)
+                ly.out_dev = hydragen_attention_decode(ly.q_dev, ly.k_dev, ly.v_dev, positions, ly.k_cache, ly.v_cache, ly.shared_ks, ly.shared_vs,
+                                                       ly.shared_cu_seq_lens, ly.shared_max_seq_lens, ly.use_varlens)
+                if after_layer is not None:
+                    after_layer(i)
+                done = torch.cuda.Event()
+                done.record(cap)
+                with torch.cuda.stream(self.d2h):
+                    self.d2h.wait_event(done)
+                    ly.out_host.copy_(ly.out_dev, non_blocking=True)
+            cap.wait_stream(self.h2d)
+            cap.wait_stream(self.d2h)
+        return graph
 
     def synchronize(self) -> None:
         self.h2d.synchronize()

@@ -114,7 +114,7 @@ int hg_rowwise_attn_fwd(const void* q, const void* k, const void* v, const void*
  * Shared-prefix attention on the 5th-generation tensor cores (tcgen05.mma, accumulators in
  * TMEM, operands staged by TMA): all sequences that share a prefix are batched into one Q
  * matrix per head and multiplied against the ONE copy of that prefix's K/V -- for EVERY shared
- * level of a hierarchy in one persistent launch.
+ * level of a hierarchy in one persistent launch (n_levels == 1 is forwarded to hg_prefix_attn_fwd's kernel).
  * Replaces, per level, flash_attention (hydragen/flash.py:284-306 -> flash-attn _flash_attn_forward, called
  * from hydragen/attention.py:270) or flash_attention_varlen (flash.py:309-351, called from
  * attention.py:313) together with the LSE transpose that follows it (attention.py:276-280,
@@ -133,7 +133,8 @@ int hg_rowwise_attn_fwd(const void* q, const void* k, const void* v, const void*
  *          out [n_q_rows, hq, d] contiguous (dtype), lse [n_q_rows, hq] fp32 (may be NULL): the level's
  *          partial result, in the layout hg_combine_lse / hg_decode_attn_fused consume.
  *   workspace    hg_prefix_workspace_bytes() bytes of device memory, zero-initialised ONCE by the caller and
- *          then owned by the library's launches: the persistent CTAs (one per SM) cut the (unit, key block)
+ *          then owned by the library's launches: where whole (group, 256-row tile, head) units would leave SMs
+ *          idle for a good part of the launch, the persistent CTAs (one per SM) cut the (unit, key block)
  *          space of all levels into equal ranges (stream-K), and a unit cut between CTAs leaves fp32
  *          partial accumulators and flags there, merged inside the same launch.  Launches that may run
  *          concurrently need separate workspaces; launches on one stream share one.  NULL: units are never
@@ -160,20 +161,41 @@ int hg_prefix_attn_grouped_fwd(const void* q, int64_t n_q_rows, int64_t q_stride
                                float sm_scale, int dtype, void* workspace, int64_t workspace_bytes,
                                void* stream);
 
-/* Bytes of workspace hg_prefix_attn_grouped_fwd / hg_prefix_attn_fwd want (independent of the problem). */
+/* Bytes of workspace hg_prefix_attn_grouped_fwd wants (independent of the problem). */
 int64_t hg_prefix_workspace_bytes(void);
 
-/* One level (the non-hierarchical case): group g owns query rows [g*q_per_group, (g+1)*q_per_group). */
+/* One level (the non-hierarchical case): group g owns query rows [g*q_per_group, (g+1)*q_per_group).  Runs the
+ * one-CTA-per-unit form of the kernel (a grid of one CTA per (group, 256-row tile, head)). */
 int hg_prefix_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
                        int n_groups, int q_per_group, int64_t n_k_rows, int k_len,
                        const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
                        int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype,
-                       void* workspace, int64_t workspace_bytes, void* stream);
+                       void* stream);
+
+/* Split-KV form of hg_prefix_attn_fwd for launches with few (group, tile, head) work items -- the
+ * head-parallel ranks of a tensor-parallel run (hydragen/tp.py:90-112) own Hq/N heads each: the keys of
+ * every group are cut into kv_splits contiguous ranges, each handled by its own CTAs, and kv_splits
+ * PARTIAL results are written back to back:
+ *   out [kv_splits, n_q_rows, hq, d],  lse [kv_splits, n_q_rows, hq]   (a split with no keys: out 0, lse -inf)
+ * to be merged by hg_combine_lse / the n_partials of hg_rowwise_attn_fwd / hg_decode_attn_fused (this is
+ * flash-attn's split-KV, whose heuristic the reference copies in hydragen/flash.py:37-73, with the reduce
+ * folded into the combine that follows anyway).  kv_splits == 1 is hg_prefix_attn_fwd. */
+int hg_prefix_attn_split_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
+                             int n_groups, int q_per_group, int64_t n_k_rows, int k_len,
+                             const int32_t* cu_seqlens_k, int max_k_len, int hq, int hkv, int d,
+                             int64_t q_stride_row, int64_t kv_stride_row, float sm_scale, int dtype,
+                             int kv_splits, void* stream);
+
+/* Suggested kv_splits (>= 1, <= max_splits) for a one-level launch on the device seen by hg_init:
+ * fills the SMs without going below 4 key blocks per CTA.  Host-side arithmetic only. */
+int hg_prefix_suggest_splits(int n_groups, int q_per_group, int hq, int max_k_len, int max_splits);
 
 /* Host-side view of the work schedule such a launch would use on a device with n_sms SMs (no device access;
  * pointers inside levels_host are ignored, a level is ragged iff max_k_len > 0).  Writes up to max_pieces
  * records of 10 int32 {cta, unit, level, head, group, row tile, first key block, end key block, split, slot}
- * and the grid size; returns the number of pieces (negative hg_status on error).  For tests and tooling. */
+ * and the grid size; returns the number of pieces (negative hg_status on error).  allow_split: 0 = whole units
+ * only (what a launch without workspace does), 1 = what a launch with workspace does (units are cut only where
+ * that shortens the launch: few units on many SMs, or a ragged last wave), 2 = always cut.  For tests and tooling. */
 int hg_prefix_schedule(const hg_prefix_level* levels_host, int n_levels, int64_t n_q_rows, int hq, int n_sms,
                        int allow_split, int32_t* pieces_out, int max_pieces, int32_t* n_ctas_out);
 

@@ -38,7 +38,7 @@ for graph in (False, True):
     if rank == 0:
         from hydragen_b200.tp import _AllReduce
 
-        nv = any(v is not None for v in _AllReduce._nvls.values())
+        nv = any(v is not None for v in _AllReduce._arenas.values())
         print(f"tp={world} graph={graph}: max |logit diff| {err:.3e} (max |logit| {scale:.2f}), NVLS all-reduce in use: {nv}", flush=True)
 torch.cuda.synchronize()
 dist.barrier()

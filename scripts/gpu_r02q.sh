@@ -1,0 +1,10 @@
+#!/bin/bash
+TAG=${1:-r02q}
+mkdir -p gpurun_out
+S=gpurun_out/summary_${TAG}.txt; : > $S
+run() { local name=$1; shift; local t=$1; shift; echo "=== $name" | tee -a $S; timeout -k 10 $t "$@" > gpurun_out/${name}_${TAG}.log 2>&1; echo "exit $? : $(tail -n 32 gpurun_out/${name}_${TAG}.log | cut -c1-220)" | tee -a $S; }
+run r01_1024 100 python scripts/time_prefix_r01.py
+run time_1024 100 python scripts/time_prefix.py
+HYDRAGEN_B200_PREFIX_DBG=32 run time_1024_sync 100 python scripts/time_prefix.py
+HYDRAGEN_B200_PREFIX_DBG=34 run time_1024_sync_delay 100 python scripts/time_prefix.py
+HYDRAGEN_B200_PREFIX_DBG=32 HG_EXTRA_NVCC_FLAGS="-DHG_PREFIX_TRACE" run trace_sync 100 python scripts/trace_prefix.py

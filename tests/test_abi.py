@@ -55,7 +55,7 @@ def test_argument_validation_without_gpu(built_lib):
     lib = _lib.load()
     rc = lib.hg_combine_lse(None, None, 0, None, None, 4, 64, 0, None)
     assert rc == -1 and b"n = 0" in lib.hg_last_error()
-    rc = lib.hg_prefix_attn_fwd(None, None, None, None, None, 1, 1, 1, 1, None, 1, 8, 8, 128, 1024, 1024, 0.1, 1, None, 0, None)
+    rc = lib.hg_prefix_attn_fwd(None, None, None, None, None, 1, 1, 1, 1, None, 1, 8, 8, 128, 1024, 1024, 0.1, 1, None)
     assert rc == -4  # hg_init not called
     args = [None] * 4 + [0, None, 1, 0, None, None, 2, 1, 4, 8, 3, 128] + [0] * 6 + [None, None, 0, 0.1, 1, None]
     rc = lib.hg_rowwise_attn_fwd(*args)
@@ -176,8 +176,10 @@ def test_header_is_plain_c_and_links(built_lib, tmp_path):
         "  if (hg_combine_lse(0, 0, 0, 0, 0, 4, 64, HG_BF16, 0) != HG_ERR_INVALID_ARGUMENT) return 3;\n"
         "  if (strstr(hg_last_error(), \"n = 0\") == 0) return 4;\n"
         "  if (hg_prefix_workspace_bytes() < 4096) return 5;\n"
+        "  if (hg_prefix_suggest_splits(1, 1024, 4, 2048, HG_MAX_COMBINE) < 1) return 8;\n"
         "  { hg_prefix_level lv; int32_t n_ctas = 0; memset(&lv, 0, sizeof lv); lv.n_groups = 1; lv.k_len = 2048;\n"
-        "    if (hg_prefix_schedule(&lv, 1, 1024, 32, 148, 1, 0, 0, &n_ctas) < 128 || n_ctas != 148) return 6; }\n"
+        "    if (hg_prefix_schedule(&lv, 1, 1024, 32, 148, 2, 0, 0, &n_ctas) < 128 || n_ctas != 148) return 6;\n"
+        "    if (hg_prefix_schedule(&lv, 1, 1024, 32, 148, 0, 0, 0, &n_ctas) != 128 || n_ctas != 128) return 7; }\n"
         '  printf("abi %d ok\\n", hg_abi_version());\n'
         "  return 0;\n}\n")
     exe = tmp_path / "abi"

@@ -243,10 +243,12 @@ def test_causal_prefill_full_size_property():
 @pytest.mark.parametrize("split", ["1", "0"])
 @pytest.mark.parametrize("ctas", [None, "5", "37"])
 def test_persistent_schedule_variants(split, ctas, monkeypatch):
-    """The persistent prefix kernel gives the oracle's result whatever the schedule: units cut between CTAs and merged
-    through the workspace (stream-K, the default) or dealt whole (HYDRAGEN_B200_PREFIX_SPLIT=0), on the full grid or on
-    a grid of 5 / 37 CTAs (HYDRAGEN_B200_PREFIX_CTAS, read once per process -> subprocess): many pieces per CTA,
-    many units per CTA, hierarchies of 2-3 levels incl. ragged ones in ONE launch."""
+    """The persistent prefix kernel (used by default for hierarchies of >= 2 shared levels; forced here for single levels
+    too with HYDRAGEN_B200_PREFIX_PERSISTENT=1) gives the oracle's result whatever the schedule: units cut between CTAs
+    and merged through the workspace (stream-K) or dealt whole (HYDRAGEN_B200_PREFIX_SPLIT=0), on the full grid or on a
+    grid of 5 / 37 CTAs (HYDRAGEN_B200_PREFIX_CTAS; the switches are read once per process -> subprocess): many pieces
+    per CTA, many units per CTA, hierarchies of 2-3 levels incl. ragged ones in ONE launch, few long units cut into many
+    pieces (the 3+-piece merge), a ragged level with an EMPTY group (out 0, lse -inf)."""
     import subprocess
 
     code = (
@@ -261,9 +263,20 @@ def test_persistent_schedule_variants(split, ctas, monkeypatch):
         "        out = hydragen_attention(**{k: dev(v) for k, v in c.items()})\n"
         "        err = (out.double().cpu() - O.hydragen_attention(**c)).abs().max().item()\n"
         "        assert err <= (1.6e-2 if dt == torch.bfloat16 else 2e-3), (sizes, rep, err)\n"
+        "from hydragen_b200.flash import flash_attention_varlen\n"
+        "for dt, qps in [(torch.float16, 40), (torch.bfloat16, 300)]:\n"
+        "    g = torch.Generator().manual_seed(qps)\n"
+        "    lens = [700, 65, 0, 130, 1]; n, hq, hkv, d = len(lens), 4, 2, 128\n"
+        "    q = torch.randn(n * qps, hq, d, generator=g).to(dt); k = torch.randn(sum(lens), hkv, d, generator=g).to(dt); v = torch.randn(sum(lens), hkv, d, generator=g).to(dt)\n"
+        "    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32); cu_q = torch.arange(0, n + 1, dtype=torch.int32) * qps\n"
+        "    out, lse = flash_attention_varlen(q.cuda(), k.cuda(), v.cuda(), cu_q.cuda(), cu.cuda(), qps, max(lens))\n"
+        "    ro, rl = O.flash_attention_varlen(q, k, v, cu_q, cu, qps, max(lens))\n"
+        "    assert (out[2 * qps:3 * qps] == 0).all() and torch.isinf(lse[2]).all()\n"
+        "    assert (out.double().cpu() - ro).abs().max().item() <= (1.6e-2 if dt == torch.bfloat16 else 2e-3)\n"
+        "    fin = torch.isfinite(rl); assert (lse.double().cpu()[fin] - rl[fin]).abs().max().item() < 5e-3\n"
         "print('schedule ok')\n"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, HYDRAGEN_B200_PREFIX_SPLIT=split)
+    env = dict(os.environ, HYDRAGEN_B200_PREFIX_SPLIT=split, HYDRAGEN_B200_PREFIX_PERSISTENT="1", HYDRAGEN_B200_PREFIX_SPLIT_OVERHEAD="0")
     if ctas is not None:
         env["HYDRAGEN_B200_PREFIX_CTAS"] = ctas
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
@@ -337,7 +350,7 @@ def test_full_size_microbenchmark_config_properties():
       2. decomposed attention == attention over the explicit concatenation [prefix ; suffix]
          computed by the row-wise kernel in one pass (the reference test's criterion,
          tests/test_attention.py:132-187), on a batch subset that fits memory;
-      3. a CPU-oracle spot check of 4 sequences."""
+      3. the CPU oracle (fp32 on the host cores) on ALL 1024 sequences and heads."""
     from hydragen_b200.attention import hydragen_attention_nopad
     from hydragen_b200.flash import flash_attention_seqlen, prefix_attention_grouped
 
@@ -368,9 +381,66 @@ def test_full_size_microbenchmark_config_properties():
     torch.cuda.synchronize()
     _assert_close(out[:nb], o_cat, torch.bfloat16, "decomposed vs concatenated")
 
-    idx = [0, 1, 511, 1023]
-    ref = O.hydragen_attention_nopad(q[idx].cpu(), k[idx].cpu(), v[idx].cpu(), [sk.cpu()], [sv.cpu()], seq_len=sl[idx].cpu(), compute_dtype=torch.float32)
-    _assert_close(out[idx], ref, torch.bfloat16, "oracle spot check")
+    ref = O.hydragen_attention_nopad(q.cpu(), k.cpu(), v.cpu(), [sk.cpu()], [sv.cpu()], seq_len=sl.cpu(), compute_dtype=torch.float32)
+    _assert_close(out, ref, torch.bfloat16, "cfg#2 full size vs oracle")
+
+
+def test_full_size_decode_config_ragged_suffix():
+    """BASELINE.json configs[2]'s decode shape at full size: B = 1024 sequences at DIFFERENT points of their completion
+    (suffix 1 .. 127 rows in a 128-row unique cache), prefix 2048, 32 heads, d = 128, bf16 -- one fused decode step
+    (KV append at positions[b] + suffix + combine behind the persistent prefix launch) against the CPU oracle on every
+    sequence, and the caches afterwards against scatter_."""
+    from hydragen_b200.attention import hydragen_attention_decode
+
+    g = torch.Generator().manual_seed(5)
+    B, Ls, Lu, H, D = 1024, 2048, 128, 32, 128
+    dt = torch.bfloat16
+    mk = lambda *s: torch.randn(*s, generator=g).to(dt)
+    q, kn, vn = mk(B, 1, H, D), mk(B, 1, H, D), mk(B, 1, H, D)
+    kc, vc = mk(B, Lu, H, D), mk(B, Lu, H, D)
+    sk, sv = mk(1, Ls, H, D), mk(1, Ls, H, D)
+    pos = torch.randint(0, Lu - 1, (B,), generator=g)
+    pos[0], pos[1] = 0, Lu - 2  # both ends: no older rows at all / 127 rows
+    kcd, vcd = kc.cuda(), vc.cuda()
+    out = hydragen_attention_decode(q.cuda(), kn.cuda(), vn.cuda(), pos.cuda(), kcd, vcd, [sk.cuda()], [sv.cuda()])
+    torch.cuda.synchronize()
+    idx = pos.view(B, 1, 1, 1).expand(B, 1, H, D)
+    kc.scatter_(1, idx, kn)
+    vc.scatter_(1, idx, vn)
+    assert torch.equal(kcd.cpu(), kc) and torch.equal(vcd.cpu(), vc)
+    ref = O.hydragen_attention_nopad(q, kc, vc, [sk], [sv], seq_len=pos + 1, compute_dtype=torch.float32)
+    _assert_close(out, ref, dt, "cfg#3 decode step, ragged suffix, full size")
+
+
+def test_full_size_two_level_hierarchy():
+    """BASELINE.json configs[3] at full size: 1 prefix of 1024 tokens -> 32 second-level prompts of 64 tokens -> 32
+    completions each (B = 1024), 32 heads, d = 128, bf16.  Both shared levels run in ONE persistent prefix launch
+    (level 2: 32 groups x 32 rows x 64 keys), merged 3-way with the suffix by the fused launch; checked against the CPU
+    oracle on every sequence and against the level-by-level result (one launch per level)."""
+    from hydragen_b200 import _lib
+    from hydragen_b200.attention import hydragen_attention_nopad
+    from hydragen_b200.flash import prefix_attention_grouped, prefix_attention_levels
+
+    g = torch.Generator().manual_seed(6)
+    B, H, D, Lu = 1024, 32, 128, 16
+    dt = torch.bfloat16
+    mk = lambda *s: torch.randn(*s, generator=g).to(dt)
+    q, k, v = mk(B, 1, H, D), mk(B, Lu, H, D), mk(B, Lu, H, D)
+    s1k, s1v, s2k, s2v = mk(1, 1024, H, D), mk(1, 1024, H, D), mk(32, 64, H, D), mk(32, 64, H, D)
+    sl = torch.randint(1, Lu + 1, (B,), generator=g)
+    n_ctas, pieces = _lib.prefix_schedule([(1, 1024, 0), (32, 64, 0)], B, H, n_sms=_lib.load().hg_sm_count() or 148)
+    assert {p[2] for p in pieces} == {0, 1}  # one launch holds units of both levels
+    qd, dev = q.cuda(), (lambda *ts: [t.cuda() for t in ts])
+    out = hydragen_attention_nopad(qd, k.cuda(), v.cuda(), dev(s1k, s2k), dev(s1v, s2v), seq_len=sl.cuda())
+    outs, lses = prefix_attention_levels(qd, dev(s1k, s2k), dev(s1v, s2v), [1, 32], [None, None], [None, None])
+    o1, l1 = prefix_attention_grouped(qd, s1k.cuda(), s1v.cuda(), n_groups=1)
+    o2, l2 = prefix_attention_grouped(qd, s2k.cuda(), s2v.cuda(), n_groups=32)
+    torch.cuda.synchronize()
+    # the grouped launch schedules differently from the single-level ones: same maths, so (nearly) the same bits
+    assert (outs[0].float() - o1.float()).abs().max().item() < 4e-3 and (lses[0] - l1).abs().max().item() < 5e-3
+    assert (outs[1].float() - o2.float()).abs().max().item() < 2e-2 and (lses[1] - l2).abs().max().item() < 5e-3
+    ref = O.hydragen_attention_nopad(q, k, v, [s1k, s2k], [s1v, s2v], seq_len=sl, compute_dtype=torch.float32)
+    _assert_close(out, ref, dt, "cfg#4 two-level hierarchy, full size")
 
 
 def test_kv_append():
@@ -455,38 +525,37 @@ def test_hydragen_attention_decode_matches_unfused(sizes):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("qps", [40, 300])
-def test_prefix_stream_k_ragged_groups(dtype, qps):
-    """Few (group, tile, head) units with ragged (varlen) key lengths: the persistent kernel cuts the long groups into
-    pieces (merged in-kernel from fp32 partials), clips pieces past a short group's end, and a group WITHOUT keys gives
-    out 0 / lse -inf.  out and LSE == oracle."""
+@pytest.mark.parametrize("splits", [2, 3, 8])
+def test_prefix_split_kv_partials_merge_to_full(dtype, splits):
+    """Split-KV prefix launch (hg_prefix_attn_split_fwd): the merged partials == the unsplit result == oracle,
+    for uniform and ragged (varlen) groups, incl. splits that receive no keys (out 0, lse -inf)."""
     from hydragen_b200 import _lib
-    from hydragen_b200.flash import flash_attention_varlen
+    from hydragen_b200.attention import combine_lse_cuda
 
-    g = torch.Generator().manual_seed(qps)
-    lens = [700, 65, 0, 130, 1]
-    n, hq, hkv, d = len(lens), 4, 2, 128
-    q = torch.randn(n * qps, hq, d, generator=g).to(dtype)
+    g = torch.Generator().manual_seed(splits)
+    lens = [700, 65, 130, 1]  # ragged groups: the short ones leave later splits empty
+    n, qps, hq, hkv, d = len(lens), 40, 4, 2, 128
+    q = torch.randn(n * qps, 1, hq, d, generator=g).to(dtype)
     k = torch.randn(sum(lens), hkv, d, generator=g).to(dtype)
     v = torch.randn(sum(lens), hkv, d, generator=g).to(dtype)
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
-    cu_q = torch.arange(0, n + 1, dtype=torch.int32) * qps
-    n_ctas, pieces = _lib.prefix_schedule([(n, 0, max(lens))], n * qps, hq)
-    assert any(p[8] for p in pieces), "this shape is meant to be split"
-    out, lse = flash_attention_varlen(q.cuda(), k.cuda(), v.cuda(), cu_q.cuda(), cu.cuda(), qps, max(lens))
+    qd, kd, vd, cud = q.cuda(), k.cuda(), v.cuda(), cu.cuda()
+    out = torch.empty(splits, n * qps, 1, hq, d, device="cuda", dtype=dtype)
+    lse = torch.empty(splits, n * qps, 1, hq, device="cuda", dtype=torch.float32)
+    _lib.prefix_attn_fwd(qd, kd, vd, out, lse, n, qps, kd.shape[0], 0, cud, max(lens), hq, hkv, d, hq * d, hkv * d, d**-0.5, kv_splits=splits)
+    merged, mlse = combine_lse_cuda([out[i] for i in range(splits)], [lse[i] for i in range(splits)], return_lse=True)
     torch.cuda.synchronize()
-    ro, rl = O.flash_attention_varlen(q, k, v, cu_q, cu, qps, max(lens))
-    empty = slice(2 * qps, 3 * qps)
-    assert (out[empty] == 0).all() and torch.isinf(lse[2]).all() and (lse[2] < 0).all()
-    _assert_close(out, ro, dtype, "stream-K ragged")
-    fin = torch.isfinite(rl)
-    assert (torch.isfinite(lse.cpu()) == fin).all()
-    assert (lse.double().cpu()[fin] - rl[fin]).abs().max().item() < 5e-3
+    assert torch.isinf(lse).any() or splits == 2  # some (group, split) pairs are empty
+    cu_q = torch.arange(0, n + 1, dtype=torch.int32) * qps
+    ro, rl = O.flash_attention_varlen(q.view(n * qps, hq, d), k, v, cu_q, cu, qps, max(lens))
+    _assert_close(merged.view(n * qps, hq, d), ro, dtype, f"split-KV x{splits}")
+    rl = rl.permute(0, 2, 1).reshape(n * qps, hq)  # [n, h, qps] -> rows
+    assert (mlse.view(n * qps, hq).double().cpu() - rl).abs().max().item() < 5e-3
 
 
-def test_operator_few_heads_is_split_and_matches():
-    """A head-parallel rank's shape (few local heads, long prefix): the schedule cuts every unit into several pieces and
-    the operator's result still matches the oracle."""
+def test_operator_uses_split_kv_when_few_heads():
+    """A head-parallel rank's shape (few local heads, long prefix): the operator picks kv_splits > 1 by itself and
+    the result still matches the oracle."""
     from hydragen_b200 import _lib
     from hydragen_b200.attention import hydragen_attention_nopad
 
@@ -495,11 +564,10 @@ def test_operator_few_heads_is_split_and_matches():
     mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16)
     q, k, v, sk, sv = mk(b, 1, hq, d), mk(b, lu, hkv, d), mk(b, lu, hkv, d), mk(1, ls, hkv, d), mk(1, ls, hkv, d)
     sl = torch.randint(1, lu + 1, (b,), generator=g)
-    n_ctas, pieces = _lib.prefix_schedule([(1, ls, 0)], b, hq)
-    assert n_ctas > 2 and all(p[8] for p in pieces)
+    assert _lib.prefix_suggest_splits(torch.device("cuda:0"), 1, b, hq, ls, 8) > 1
     out = hydragen_attention_nopad(q.cuda(), k.cuda(), v.cuda(), [sk.cuda()], [sv.cuda()], seq_len=sl.cuda())
     ref = O.hydragen_attention_nopad(q, k, v, [sk], [sv], seq_len=sl)
-    _assert_close(out, ref, torch.bfloat16, "stream-K, few heads")
+    _assert_close(out, ref, torch.bfloat16, "auto split-KV")
 
 
 def test_host_decode_pipeline_matches_direct_calls():
@@ -534,4 +602,20 @@ def test_host_decode_pipeline_matches_direct_calls():
             ref = hydragen_attention_decode(ly.q_host.cuda(), ly.k_host.cuda(), ly.v_host.cuda(), pos, kc, vc, [sk], [sv])
             torch.cuda.synchronize()
             assert torch.equal(ly.out_host, ref.cpu())
+            assert torch.equal(ly.k_cache, kc) and torch.equal(ly.v_cache, vc)
+    # the same step captured once as a CUDA graph (copies + kernels of every layer on the three streams) and replayed
+    pos = torch.full((b,), 3, dtype=torch.int64, device=dev)  # static device tensor: updated in place between replays
+    graph = pipe.capture(layers, pos)
+    for step in range(3, 6):
+        pos.fill_(step)
+        for ly in layers:
+            ly.q_host.copy_(mk(b, 1, hq, d))
+            ly.k_host.copy_(mk(b, 1, hkv, d))
+            ly.v_host.copy_(mk(b, 1, hkv, d))
+        graph.replay()
+        torch.cuda.synchronize()
+        for ly, (kc, vc, sk, sv) in zip(layers, ref_state):
+            ref = hydragen_attention_decode(ly.q_host.cuda(), ly.k_host.cuda(), ly.v_host.cuda(), pos, kc, vc, [sk], [sv])
+            torch.cuda.synchronize()
+            assert torch.equal(ly.out_host, ref.cpu()), f"graphed step {step}"
             assert torch.equal(ly.k_cache, kc) and torch.equal(ly.v_cache, vc)

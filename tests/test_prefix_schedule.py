@@ -38,7 +38,7 @@ def _units(levels, n_q_rows, hq):
 @pytest.mark.parametrize("n_sms", [148, 7, 1])
 def test_stream_k_schedule_tiles_every_unit_exactly_once(name, n_sms, built_lib):
     levels, n_q_rows, hq = CASES[name]
-    n_ctas, pieces = _lib.prefix_schedule(levels, n_q_rows, hq, n_sms=n_sms, allow_split=True)
+    n_ctas, pieces = _lib.prefix_schedule(levels, n_q_rows, hq, n_sms=n_sms, allow_split=2)
     nbs = _units(levels, n_q_rows, hq)
     assert 1 <= n_ctas <= n_sms
     covered = collections.defaultdict(list)
@@ -79,11 +79,20 @@ def test_whole_unit_schedule(name, built_lib):
     assert all(p[8] == 0 and p[6] == 0 and p[7] == nbs[p[1]] and p[0] == p[1] % n_ctas for p in pieces)
 
 
-def test_cfg2_uses_every_sm(built_lib):
-    """The round-1 launch had 128 CTAs on 148 SMs; the stream-K schedule keeps all 148 busy with equal shares."""
-    n_ctas, pieces = _lib.prefix_schedule(*CASES["cfg2"])
+def test_stream_k_balances_cfg2_over_every_sm(built_lib):
+    """Forced stream-K at cfg#2: all 148 SMs get equal shares of the 128 x 32 key blocks."""
+    n_ctas, pieces = _lib.prefix_schedule(*CASES["cfg2"], allow_split=2)
     assert n_ctas == 148
     blocks = collections.Counter()
     for p in pieces:
         blocks[p[0]] += p[7] - p[6]
     assert max(blocks.values()) - min(blocks.values()) <= 8 and sum(blocks.values()) == 128 * 32
+
+
+def test_units_are_cut_only_where_it_pays(built_lib):
+    """The launch's own choice (allow_split=1): cutting units costs about 6 key blocks on the critical path (measured), so
+    cfg#2's 128 units on 148 SMs stay whole (32 blocks vs 27.7 + 6), while few long units (cfg#5 per GPU, the ranks of a
+    TP run) and a ragged last wave (B = 4096: 3.46 waves) are cut."""
+    split = lambda name: any(p[8] for p in _lib.prefix_schedule(*CASES[name], allow_split=1)[1])
+    assert not split("cfg2") and not split("cfg4_two_levels")
+    assert split("cfg5_per_gpu") and split("tp8_rank_of_cfg2") and split("cfg2_b4096") and split("one_head")
