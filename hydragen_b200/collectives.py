@@ -18,7 +18,7 @@ from . import _lib
 
 
 class MultimemAllReduce:
-    def __init__(self, nbytes: int, device: torch.device, group=None, n_blocks: int = 32):
+    def __init__(self, nbytes: int, device: torch.device, group=None, n_blocks: int = 16):
         """Collective over ``group`` (default: world) for messages carved out of one symmetric arena of ``nbytes``."""
         import torch.distributed._symmetric_memory as symm_mem
 
