@@ -2,9 +2,8 @@
 # ncu captures of the shipped kernels (full set, with source) + launch list of the bench command
 TAG=${1:-r02w}
 mkdir -p gpurun_out
-prof() { local name=$1; local rx=$2; shift; shift; timeout 600 ncu --set full --clock-control none --import-source on -k regex:$rx -s 6 -c 2 -f -o gpurun_out/prof_${name}_${TAG} "$@" > gpurun_out/ncu_${name}_${TAG}.log 2>&1; echo "$name: ncu exit $?"; }
+prof() { local name=$1; local rx=$2; shift; shift; timeout 600 ncu --set full --clock-control none --import-source on -k regex:$rx -s 2 -c 2 -f -o gpurun_out/prof_${name}_${TAG} "$@" > gpurun_out/ncu_${name}_${TAG}.log 2>&1; echo "$name: ncu exit $?"; }
 prof prefix_unit prefix_unit python scripts/ncu_hierarchy.py
 prof prefix_grouped prefix_attn_sm100 python scripts/ncu_hierarchy.py
 prof decode_slot decode_slot python scripts/ncu_hierarchy.py
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --e2e-steps 0 --no-cpu-baseline --no-sweep --no-lib --no-full-model --sustain-seconds 0 > gpurun_out/ncu_launches_${TAG}.log 2>&1; echo "launch list: exit $?"
 ls -la gpurun_out/*${TAG}*
