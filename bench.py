@@ -22,7 +22,8 @@ lightest point of a decode (suffix 1); the projections / MLP / sampling around i
   `decode_integrated`  attention time of an average step of BASELINE.json configs[2] (suffix 1..127), from the sweep;
   `full_model`         configs[2] itself: random-init Llama-2-7B generate(1024 x 128 tokens), whole-model tokens/s;
   `sustained`          the same step replayed for seconds, against the sustained cuBLAS peak, with clocks;
-  `lib_fa2`            the installed flash-attn 2.x kernels on the same tensors (the library the reference calls).
+  `lib_fa2`            the installed flash-attn 2.x kernels on the same tensors (the library the reference calls);
+  `hierarchy_cfg4`     configs[3]: the two-level hierarchy 1 x 1024 -> 32 x 64 -> B = 1024, one grouped prefix launch per layer.
 
 Multi-GPU = the reference's head-axis tensor parallelism (hydragen/tp.py): each rank runs the same
 step on Hq/N local heads, then per layer ONE all-reduce of the [B, hidden] bf16 tensor that
@@ -635,6 +636,17 @@ def run_ours(a):
                         "sample": f"1 of {L} layers of the same workload, fp32 torch, median of {n} runs (~{a.cpu_seconds:.0f} s); tokens/s extrapolated x{L}",
                         "ms_per_layer": t_layer * 1e3}
 
+    # ---- BASELINE.json configs[3] at the operator level: two shared levels in one grouped prefix launch ----------
+    hierarchy = None
+    if world == 1 and not a.no_sweep:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        try:
+            import time_hierarchy
+
+            hierarchy = time_hierarchy.run(peaks=peaks or None)
+        except Exception as ex:
+            hierarchy = {"error": repr(ex)[:300]}
+
     used_graph = graph is not None
     full_model = None
     if world == 1 and not a.no_full_model:
@@ -663,6 +675,7 @@ def run_ours(a):
             "roofline": roofline, "roofline_suffix": roofline_suffix, "roofline_rope": roofline_rope, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
             "sustained": sustained, "suffix_sweep": suffix_sweep, "decode_integrated": decode_integrated, "lib_fa2": lib_fa2,
+            "hierarchy_cfg4": hierarchy,
         }
         if full_model is not None:
             line["full_model"] = full_model
