@@ -74,6 +74,12 @@ SYMBOLS = {
          _c_void_pp, _c_void_pp, c_int, c_float, c_int, c_void_p],
     ),
     "hg_allreduce_multimem": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
+    "hg_oproj_allreduce_fwd": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_int64, c_int64, c_int,
+         c_int, c_void_p],
+    ),
+    "hg_oproj_allreduce_flag_words": (c_int, [c_int64, c_int64, c_int]),
     "hg_kv_append": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
@@ -314,6 +320,24 @@ def allreduce_multimem(mc_ptr: int, out_ptr: int, flags_dev: int, rank: int, wor
         rc = load().hg_allreduce_multimem(c_void_p(mc_ptr), c_void_p(out_ptr), c_void_p(flags_dev), rank, world, nbytes, dtype_code(dtype), n_blocks,
                                           c_void_p(torch.cuda.current_stream(device).cuda_stream))
     _check(rc, "hg_allreduce_multimem")
+
+
+def oproj_allreduce_flag_words(m: int, n: int, world: int) -> int:
+    return int(load().hg_oproj_allreduce_flag_words(m, n, world))
+
+
+def oproj_allreduce_fwd(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, out_mc: int = 0, flags_dev: int = 0, flag_words: int = 0,
+                        rank: int = 0, world: int = 1, n_ctas: int = 0) -> None:
+    """out[m, n] = sum over ranks of x[m, k] @ w[n, k]^T (hg_oproj_allreduce_fwd; world == 1: the tcgen05 GEMM alone)."""
+    ensure_init(x.device)
+    if x.dim() != 2 or w.dim() != 2 or out.dim() != 2 or x.shape[1] != w.shape[1] or out.shape != (x.shape[0], w.shape[0]):
+        raise ValueError(f"oproj_allreduce: x {tuple(x.shape)}, w {tuple(w.shape)}, out {tuple(out.shape)}")
+    if not (x.dtype == w.dtype == out.dtype) or x.stride(1) != 1 or w.stride(1) != 1 or not out.is_contiguous():
+        raise ValueError("oproj_allreduce: one 16-bit dtype, unit inner strides, contiguous out")
+    with torch.cuda.device(x.device):
+        rc = load().hg_oproj_allreduce_fwd(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(out), c_void_p(out_mc), c_void_p(flags_dev),
+                                           flag_words, rank, world, x.shape[0], w.shape[0], x.shape[1], dtype_code(x.dtype), n_ctas, _stream(x))
+    _check(rc, "hg_oproj_allreduce_fwd")
 
 
 def rope_qk(q, k, q_out, k_out, cos_table, sin_table, positions, rows, hq, hkv, d, q_stride_row, k_stride_row,

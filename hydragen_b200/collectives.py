@@ -17,6 +17,9 @@ import torch.distributed as dist
 from . import _lib
 
 
+GEMM_FLAG_WORDS = 16384  # enough for 2032 output tiles of 128 x 256 at 8 ranks
+
+
 class MultimemAllReduce:
     def __init__(self, nbytes: int, device: torch.device, group=None, n_blocks: int = 16):
         """Collective over ``group`` (default: world) for messages carved out of one symmetric arena of ``nbytes``."""
@@ -33,8 +36,14 @@ class MultimemAllReduce:
         self.flags = symm_mem.empty(128, dtype=torch.int32, device=device)
         self.flags.zero_()
         self._hf = symm_mem.rendezvous(self.flags, name)
+        # flag words of csrc/oproj_allreduce.cu (the GEMM fused with this collective): its own array -- per-tile arrival
+        # epochs, 128 + tiles * world words
+        self.gemm_flags = symm_mem.empty(GEMM_FLAG_WORDS, dtype=torch.int32, device=device)
+        self.gemm_flags.zero_()
+        self._hg = symm_mem.rendezvous(self.gemm_flags, name)
         self.mc_base = int(self._h.multicast_ptr or 0)  # 0: no multicast mapping on this platform
         self.flags_dev = int(self._hf.buffer_ptrs_dev)
+        self.gemm_flags_dev = int(self._hg.buffer_ptrs_dev)
         torch.cuda.synchronize(device)
         dist.barrier(self.group)
         self._used = 0
@@ -63,6 +72,19 @@ class MultimemAllReduce:
         assert self.available, "no NVLink multicast mapping on this platform: use torch.distributed.all_reduce"
         _lib.allreduce_multimem(self.mc_base + off, 0, self.flags_dev, self.rank, self.world, nbytes, t.dtype, self.n_blocks, self.device)
         return t
+
+    def linear_all_reduce_(self, x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, n_ctas: int = 0) -> torch.Tensor:
+        """out = sum over the group of x @ w.T in ONE launch (csrc/oproj_allreduce.cu): x [m, k] this rank's attention
+        output, w [n, k] its slice of o_proj.weight, out [m, n] from ``buffer()`` -- hydragen/llama.py:592-594 followed by
+        hydragen/tp.py:108-112."""
+        off = out.data_ptr() - self.arena.data_ptr()
+        nbytes = out.numel() * out.element_size()
+        assert 0 <= off and off + nbytes <= self.arena.numel() and out.is_contiguous(), "out must come from buffer()"
+        assert self.available, "no NVLink multicast mapping on this platform"
+        if _lib.oproj_allreduce_flag_words(x.shape[0], w.shape[0], self.world) > GEMM_FLAG_WORDS:
+            raise ValueError(f"linear_all_reduce_: [{x.shape[0]}, {w.shape[0]}] has too many tiles for {GEMM_FLAG_WORDS} flag words")
+        _lib.oproj_allreduce_fwd(x, w, out, self.mc_base + off, self.gemm_flags_dev, GEMM_FLAG_WORDS, self.rank, self.world, n_ctas)
+        return out
 
     def all_reduce(self, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Out-of-place sum (one-shot form: one cross-rank barrier): ``t`` from ``buffer()``, result in a private

@@ -1,6 +1,7 @@
 // C ABI of hydragen_b200 (see include/hydragen_b200.h): argument validation, error plumbing and
 // device bring-up.  No torch types, no allocation, no synchronisation on any launch path.
 #include <cstdarg>
+#include <cstdint>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -353,6 +354,41 @@ int hg_allreduce_multimem(void* mc_ptr, void* out, const void* flags_dev, int ra
   if (n_blocks < 1 || n_blocks > 1024) return set_error(HG_ERR_INVALID_ARGUMENT, "allreduce: n_blocks = %d", n_blocks);
   if (nbytes == 0) return HG_OK;
   return launch_allreduce_multimem(mc_ptr, out, flags_dev, rank, world, nbytes, dtype, n_blocks, (cudaStream_t)stream);
+}
+
+int hg_oproj_allreduce_flag_words(int64_t m, int64_t n, int world) {
+  if (m < 0 || n < 0 || world < 1) return 0;
+  return oproj_allreduce_flag_words(m, n, world);
+}
+
+int hg_oproj_allreduce_fwd(const void* x, int64_t x_stride_row, const void* w, int64_t w_stride_row, void* out, void* out_mc,
+                           const void* flags_dev, int64_t flag_words, int rank, int world, int64_t m, int64_t n, int64_t k, int dtype,
+                           int n_ctas, void* stream) {
+  if (dtype != HG_BF16 && dtype != HG_F16) return set_error(HG_ERR_UNSUPPORTED, "oproj_allreduce: 16-bit types only (dtype %d)", dtype);
+  if (world < 1 || world > 32 || rank < 0 || rank >= world) return set_error(HG_ERR_INVALID_ARGUMENT, "oproj_allreduce: rank %d of %d", rank, world);
+  if (m < 0 || n < 1 || k < 1 || m > INT32_MAX || n > INT32_MAX || k > INT32_MAX)
+    return set_error(HG_ERR_INVALID_ARGUMENT, "oproj_allreduce: bad sizes m=%lld n=%lld k=%lld", (long long)m, (long long)n, (long long)k);
+  if (n % 8 != 0 || k % 8 != 0 || x_stride_row % 8 != 0 || w_stride_row % 8 != 0 || x_stride_row < k || w_stride_row < k)
+    return set_error(HG_ERR_UNSUPPORTED, "oproj_allreduce: n, k and the row strides must be multiples of 8 elements (16 bytes), strides >= k");
+  if (m == 0 && world == 1) return HG_OK;
+  if (x == nullptr || w == nullptr || out == nullptr) return set_error(HG_ERR_INVALID_ARGUMENT, "oproj_allreduce: null pointer");
+  if (reinterpret_cast<uintptr_t>(x) % 16 || reinterpret_cast<uintptr_t>(w) % 16 || reinterpret_cast<uintptr_t>(out) % 16 ||
+      reinterpret_cast<uintptr_t>(out_mc) % 16)
+    return set_error(HG_ERR_UNSUPPORTED, "oproj_allreduce: pointers must be 16-byte aligned");
+  if (world > 1) {
+    if (out_mc == nullptr || flags_dev == nullptr) return set_error(HG_ERR_INVALID_ARGUMENT, "oproj_allreduce: null multicast / flag pointer");
+    if (m == 0) return set_error(HG_ERR_INVALID_ARGUMENT, "oproj_allreduce: empty message in a collective call");
+    if (flag_words < oproj_allreduce_flag_words(m, n, world))
+      return set_error(HG_ERR_INVALID_ARGUMENT, "oproj_allreduce: %lld flag words, this shape needs %d", (long long)flag_words,
+                       oproj_allreduce_flag_words(m, n, world));
+  }
+  if (n_ctas < 0) return set_error(HG_ERR_INVALID_ARGUMENT, "oproj_allreduce: n_ctas = %d", n_ctas);
+  OprojParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.w = w; p.out = out; p.out_mc = out_mc; p.flags_dev = flags_dev;
+  p.m = m; p.n = n; p.k = k; p.x_stride_row = x_stride_row; p.w_stride_row = w_stride_row;
+  p.rank = rank; p.world = world; p.dtype = dtype; p.n_ctas = n_ctas;
+  return launch_oproj_allreduce(p, (cudaStream_t)stream);
 }
 
 int hg_kv_append(const void* k_new, const void* v_new, const void* positions, int positions_i64, void* k_cache, void* v_cache,

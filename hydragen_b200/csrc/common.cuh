@@ -196,6 +196,19 @@ int suggest_prefix_splits(int n_groups, int q_per_group, int hq, int max_k_len, 
 int launch_allreduce_multimem(void* mc_ptr, void* out, const void* flags_dev, int rank, int world, int64_t nbytes, int dtype,
                               int n_blocks, cudaStream_t s);
 
+// o_proj GEMM fused with its all-reduce (oproj_allreduce.cu)
+struct OprojParams {
+  const void* x;  // [m, k], row stride x_stride_row
+  const void* w;  // [n, k], row stride w_stride_row
+  void* out;      // [m, n] contiguous: this rank's symmetric buffer (world > 1) or any buffer (world == 1)
+  void* out_mc;   // multicast address of the same buffer (world > 1)
+  const void* flags_dev;
+  int64_t m, n, k, x_stride_row, w_stride_row;
+  int rank, world, dtype, n_ctas;
+};
+int launch_oproj_allreduce(const OprojParams& p, cudaStream_t s);
+int oproj_allreduce_flag_words(int64_t m, int64_t n, int world);
+
 int launch_kv_append(const void* k_new, const void* v_new, const void* positions, int positions_i64, void* k_cache,
                      void* v_cache, int b, int nq, int lk, int hkv, int d, int dtype, cudaStream_t s);
 

@@ -269,6 +269,31 @@ int hg_allreduce_multimem(void* mc_ptr, void* out, const void* flags_dev, int ra
                           int64_t nbytes, int dtype, int n_blocks, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Row-parallel o_proj GEMM fused with the all-reduce that follows it ("next" row N4 of SURVEY.md 8f): replaces
+ * self.o_proj(attn_output) at hydragen/llama.py:592-594 on the column slice of the weight a rank holds
+ * (hydragen/tp.py:99, RowwiseParallel) plus the funcol.all_reduce of hydragen/tp.py:108-112, in one persistent launch:
+ * tcgen05 GEMM tiles written to this rank's symmetric buffer, per-tile "in place" flags raised in the owning rank's
+ * memory, in-switch reduction (multimem.ld_reduce / multimem.st) of each tile as soon as every rank has produced it.
+ *   x [m, k]      this rank's attention output (k = local heads * head_dim), row stride x_stride_row (elements)
+ *   w [n, k]      this rank's slice of o_proj.weight (torch Linear layout: out_features x in_features), row stride w_stride_row
+ *   out [m, n]    contiguous; world > 1: inside this rank's symmetric allocation, at the same offset on every rank;
+ *                 holds sum over ranks of x_r w_r^T on return (rounded to `dtype` once per rank and once after the sum,
+ *                 accumulated in fp32 -- exactly what a library GEMM followed by hg_allreduce_multimem produces)
+ *   out_mc        multicast address of `out` (world > 1; else ignored)
+ *   flags_dev     DEVICE array of `world` pointers to the ranks' flag arrays for THIS entry point (uint32, zeroed once,
+ *                 peer-accessible; not shared with hg_allreduce_multimem); flag_words = their length, at least
+ *                 hg_oproj_allreduce_flag_words(m, n, world).  Word 0: epoch; 1: CTA count; 32+p: "rank p's slices written
+ *                 everywhere"; 128 + tile*world + p: "rank p's partial of tile `tile` is in place" (used in the owner's copy)
+ *   world == 1    the GEMM alone (out_mc / flags_dev ignored)
+ *   n_ctas        0 = one CTA per SM; else that many (<= SM count: the CTAs of a launch must be co-resident)
+ * n, k and the row strides must be multiples of 8; dtype HG_BF16 / HG_F16.  Every rank of the group must enqueue the same
+ * call (same m, n, world) in the same order.  CUDA-graph capturable. */
+int hg_oproj_allreduce_fwd(const void* x, int64_t x_stride_row, const void* w, int64_t w_stride_row, void* out,
+                           void* out_mc, const void* flags_dev, int64_t flag_words, int rank, int world, int64_t m,
+                           int64_t n, int64_t k, int dtype, int n_ctas, void* stream);
+int hg_oproj_allreduce_flag_words(int64_t m, int64_t n, int world);
+
+/* ---------------------------------------------------------------------------------------
  * Rotary position embedding of the new q and k rows in one launch ("next" row N2 of SURVEY.md 8f): the
  * step right before the hot path.  Replaces apply_rotary_pos_emb as called at hydragen/llama.py:494-501
  * (transformers 4.37.2: cos[position_ids].unsqueeze(2); x * cos + rotate_half(x) * sin for q and for k --
