@@ -37,19 +37,32 @@ namespace hg {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int kStages = 3;
-constexpr int kThreads = 256;                 // warps 0-3 epilogue (TMEM lane quarter = warp), 4 TMA, 5 MMA, 6-7 phase 2 only
-constexpr int kABytes = BM * BK * 2;          // one TMA box: 128 rows x 128 B
-constexpr int kBBytes = BN * BK * 2;          // one TMA box: 256 rows x 128 B
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kBoxBytes = BM * 64 * 2;        // one output box: 128 rows x 64 columns
-constexpr int kStagingBytes = BM * BN * 2;    // 4 output boxes
-constexpr int kOffStaging = kStages * kStageBytes;
-constexpr int kOffBars = kOffStaging + kStagingBytes;
-constexpr int kSmemBytes = kOffBars + 256 + 1024;  // + alignment slack
-constexpr uint32_t kTmemCols = 512;           // two 128 x 256 fp32 accumulators
-constexpr int kUnitRows = 16;                 // rows of a tile reduced by one CTA at a time (2 per warp)
+constexpr int BM = 128, BK = 64;
+constexpr int kGemmWarps = 6;    // warps 0-3 epilogue (TMEM lane quarter = warp), 4 TMA, 5 MMA
+constexpr int kMaxReduceWarps = 8;  // warps 6...: phase 2, running beside phase 1 (how many is a launch parameter)
+constexpr int kThreads = (kGemmWarps + kMaxReduceWarps) * 32;
+constexpr int kABytes = BM * BK * 2;    // one TMA box: 128 rows x 128 B
+constexpr int kBoxBytes = BM * 64 * 2;  // one output box: 128 rows x 64 columns
+constexpr int kU = 4;                   // reductions in flight per lane and slice (and as many again prefetched)
+
+// BN = 256: three 48 KiB ring slots; BN = 128: five 32 KiB slots.  Narrow tiles cost a third more operand traffic but
+// finish in more, shorter waves -- which is what lets the reduction start early when the whole product is one wave wide.
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = BN == 256 ? 3 : 5;
+  static constexpr int kBBytes = BN * BK * 2;  // one TMA box: BN rows x 128 B
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = BM * BN * 2;  // BN / 64 output boxes
+  static constexpr int kOffStaging = kStages * kStageBytes;
+  static constexpr int kOffBars = kOffStaging + kStagingBytes;
+  static constexpr int kSmemBytes = kOffBars + 256 + 1024;  // + alignment slack
+  static constexpr uint32_t kTmemCols = 2 * BN;             // two 128 x BN fp32 accumulators
+  static constexpr int kLanesPerRow = BN / 8;               // 16-byte vectors in a tile row
+  static constexpr int kRowsPerInst = 32 / kLanesPerRow;    // tile rows one warp-wide reduction covers
+  static constexpr int kUnitRows = kU * kRowsPerInst;       // rows of a tile one warp reduces at a time
+  static constexpr int kUnitsPerTile = BM / kUnitRows;
+};
+constexpr int kMaxStages = 5;
 
 // flag words of a rank (uint32, zeroed once, in its own symmetric flag array; written remotely, polled at home)
 constexpr int kWEpoch = 0;    // calls completed by this rank (local)
@@ -58,15 +71,12 @@ constexpr int kWOut = 32;     // + p: "rank p's slices of call e are written eve
 constexpr int kWReady = 128;  // + tile * world + p: "rank p's partial of tile `tile`, call e, is in place" (owner's copy only)
 
 struct Barriers {
-  uint64_t full[kStages], empty[kStages];
+  uint64_t full[kMaxStages], empty[kMaxStages];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
   uint32_t last;
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -106,13 +116,14 @@ __device__ __forceinline__ void mc_st(uint4* p, const uint4& v) {
 
 #ifdef HG_OPROJ_TRACE
 // Development aid: %globaltimer stamps [CTA][stage] of the most recent call.  0 entry, 1 dependency wait passed,
-// 2 first accumulator complete, 3 last tile stored and signalled, 4 first slice's flags seen, 5 phase 2 done, 6 fence done,
-// 7 (last CTA) end barrier passed
-__device__ long long g_oproj_trace[160 * 8];
+// 2 first accumulator complete, 3 last tile stored and signalled, 4 first slice's flags seen (reduce warp 0), 5 reduce warp 0
+// done, 6 fence done, 7 (last CTA) end barrier passed, 8 first tile signalled, 9 reduce warp 0: first slice multicast,
+// 10 MMA warp done
+__device__ long long g_oproj_trace[160 * 16];
 __device__ __forceinline__ void op_stamp(int stage) {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  g_oproj_trace[blockIdx.x * 8 + stage] = t;
+  g_oproj_trace[blockIdx.x * 16 + stage] = t;
 }
 #define HG_OSTAMP(cond, stage) \
   do {                         \
@@ -126,22 +137,23 @@ __device__ __forceinline__ void op_stamp(int stage) {
 
 }  // namespace
 
-template <typename T>
+template <typename T, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
     oproj_allreduce_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                                  const __grid_constant__ CUtensorMap tmap_out, uint4* __restrict__ mc,
-                                 uint32_t* const* __restrict__ flags, int rank, int world, int M, int N, int K) {
+                                 uint32_t* const* __restrict__ flags, int rank, int world, int M, int N, int K, int signal_mode) {
+  using C = Cfg<BN>;
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t kIdesc = make_idesc(kFmt, 0, BM, BN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  Barriers* bars = reinterpret_cast<Barriers*>(smem + kOffBars);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + C::kOffBars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + BM - 1) / BM, n_tiles = m_tiles * ((N + BN - 1) / BN), n_kb = (K + BK - 1) / BK;
 
   HG_OSTAMP(threadIdx.x == 0, 0);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < C::kStages; ++i) {
       mbar_init(&bars->full[i], 1);
       mbar_init(&bars->empty[i], 1);
     }
@@ -152,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     fence_barrier_init();
   }
   if (warp == 5) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(C::kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -168,22 +180,23 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* mine = world > 1 ? flags[rank] : nullptr;
   const uint32_t e = world > 1 ? ld_volatile_u32(mine + kWEpoch) + 1u : 0u;  // stable for the whole call
 
-  // ====================================== phase 1: the GEMM tiles of this CTA =============================================
   if (warp == 4) {
+    // ====================================== phase 1: TMA producer ========================================================
     if (elect_one()) {
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int mt = tile % m_tiles, nt = tile / m_tiles;
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
-          const int st = it % kStages;
-          mbar_wait(&bars->empty[st], ((it / kStages) & 1) ^ 1);
-          mbar_expect_tx(&bars->full[st], kStageBytes);
-          tma_load_2d(smem + st * kStageBytes, &tmap_x, kb * BK, mt * BM, &bars->full[st]);
-          tma_load_2d(smem + st * kStageBytes + kABytes, &tmap_w, kb * BK, nt * BN, &bars->full[st]);
+          const int st = it % C::kStages;
+          mbar_wait(&bars->empty[st], ((it / C::kStages) & 1) ^ 1);
+          mbar_expect_tx(&bars->full[st], C::kStageBytes);
+          tma_load_2d(smem + st * C::kStageBytes, &tmap_x, kb * BK, mt * BM, &bars->full[st]);
+          tma_load_2d(smem + st * C::kStageBytes + kABytes, &tmap_w, kb * BK, nt * BN, &bars->full[st]);
         }
       }
     }
   } else if (warp == 5) {
+    // ====================================== phase 1: MMA issuer ==========================================================
     const bool leader = elect_one();
     constexpr uint32_t kHi = desc_hi(1024);  // SWIZZLE_128B, K-major: 8-row groups 1024 B apart
     const uint32_t a_lo0 = desc_lo(smem_u32(smem), 0), b_lo0 = desc_lo(smem_u32(smem + kABytes), 0);
@@ -194,11 +207,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_after();
       const uint32_t d_tmem = tmem + (uint32_t)acc * BN;
       for (int kb = 0; kb < n_kb; ++kb, ++it) {
-        const int st = it % kStages;
-        mbar_wait(&bars->full[st], (it / kStages) & 1);
+        const int st = it % C::kStages;
+        mbar_wait(&bars->full[st], (it / C::kStages) & 1);
         tc_fence_after();
         if (leader) {
-          const uint32_t a_lo = a_lo0 + st * (kStageBytes >> 4), b_lo = b_lo0 + st * (kStageBytes >> 4);
+          const uint32_t a_lo = a_lo0 + st * (C::kStageBytes >> 4), b_lo = b_lo0 + st * (C::kStageBytes >> 4);
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) umma_ss(d_tmem, a_lo + kk * 2, kHi, b_lo + kk * 2, kHi, kIdesc, (kb > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&bars->empty[st]);
@@ -207,8 +220,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         __syncwarp();
       }
     }
+    HG_OSTAMP(lane == 0, 10);
   } else if (warp < 4) {
-    uint8_t* staging = smem + kOffStaging;
+    // ====================================== phase 1: epilogue ============================================================
+    uint8_t* staging = smem + C::kOffStaging;
     const int row = warp * 32 + lane;
     int lt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
@@ -247,88 +262,99 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       named_bar_sync<1, 128>();  // staging may be overwritten
       if (threadIdx.x == 0 && world > 1) {
-        bulk_wait_all();  // the tile is in this GPU's L2, where the switch's reads find it
-        st_release_sys(flags[tile % world] + kWReady + tile * world + rank, e);
+        // The tile must be in this GPU's L2 -- the point of coherence the switch's reads go through -- before the flag
+        // leaves.  Completion of the bulk store alone does not guarantee that (r02zc: stale tiles read), a gpu-scope fence
+        // does; a SYSTEM-scope release is not needed for data that stays at home, and costs dearly here: it queues behind
+        // the multicast stores the reduce warps next door have in flight (r02za trace: 12 us from accumulator to flag).
+        bulk_wait_all();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        if (signal_mode == 1) __threadfence();
+        if (signal_mode == 2) __threadfence_system();
+        st_relaxed_sys(flags[tile % world] + kWReady + tile * world + rank, e);
+        HG_OSTAMP(lt == 0, 8);
       }
     }
     if (threadIdx.x == 0) {
       bulk_wait_all();
       HG_OSTAMP(true, 3);
     }
+  } else if (world > 1) {
+    // ====================================== phase 2: reduce the slices this rank owns ====================================
+    // Runs BESIDE phase 1 on warps of its own: slices become reducible tile by tile, in the order the tiles are produced
+    // (every rank walks the tiles in the same order), so the switch starts working while later tiles are still being
+    // multiplied.  Each warp is on its own -- no CTA-wide barrier: lanes < world poll the tile's flags, the warp converges,
+    // then every lane keeps kU reductions in flight and issues the next slice's before it multicasts this one's (the two
+    // load opposite link directions).
+    const int n_own = (n_tiles - rank + world - 1) / world;  // tiles rank, rank + world, ...
+    const int n_units = n_own * C::kUnitsPerTile;
+    const int64_t row_vecs = (int64_t)N / 8;  // 16-byte vectors per output row
+    const int stride = gridDim.x * ((int)(blockDim.x >> 5) - kGemmWarps);
+    int polled = -1;
+    // all flags of the slice's tile carry this call's epoch (">= e": a fast peer may already be in the next call)
+    auto wait_ready = [&](int tile) {
+      if (tile == polled) return;
+      if (lane < world) {
+        const uint32_t* f = mine + kWReady + tile * world + lane;
+        while ((int32_t)(ld_acquire_sys(f) - e) < 0) __nanosleep(64);
+      }
+      __syncwarp();
+      polled = tile;
+    };
+    // slice u: kUnitRows rows x BN columns of an owned tile; instruction j of the warp covers kRowsPerInst of its rows
+    auto unit_addr = [&](int u, int j, bool& ok) -> uint4* {
+      const int tile = rank + (u / C::kUnitsPerTile) * world;
+      const int mt = tile % m_tiles, nt = tile / m_tiles;
+      const int r = mt * BM + (u % C::kUnitsPerTile) * C::kUnitRows + j * C::kRowsPerInst + lane / C::kLanesPerRow;
+      const int c = nt * BN + (lane % C::kLanesPerRow) * 8;
+      ok = r < M && c < N;
+      return mc + (int64_t)r * row_vecs + (c >> 3);
+    };
+    // warp w of CTA b starts at slice w * gridDim.x + b: the slices of the earliest tiles are spread over all SMs
+    int u = (warp - kGemmWarps) * gridDim.x + blockIdx.x;
+    uint4 cur[kU], nxt[kU];
+    if (u < n_units) {
+      wait_ready(rank + (u / C::kUnitsPerTile) * world);
+      HG_OSTAMP(warp == kGemmWarps && lane == 0, 4);
+#pragma unroll
+      for (int j = 0; j < kU; ++j) {
+        bool ok;
+        uint4* p = unit_addr(u, j, ok);
+        if (ok) cur[j] = mc_ld_reduce<T>(p);
+      }
+    }
+    while (u < n_units) {
+      const int u2 = u + stride;
+      if (u2 < n_units) {
+        wait_ready(rank + (u2 / C::kUnitsPerTile) * world);
+#pragma unroll
+        for (int j = 0; j < kU; ++j) {
+          bool ok;
+          uint4* p = unit_addr(u2, j, ok);
+          if (ok) nxt[j] = mc_ld_reduce<T>(p);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kU; ++j) {
+        bool ok;
+        uint4* p = unit_addr(u, j, ok);
+        if (ok) mc_st(p, cur[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kU; ++j) cur[j] = nxt[j];
+      HG_OSTAMP(warp == kGemmWarps && lane == 0 && u < stride, 9);
+      u = u2;
+    }
+    HG_OSTAMP(warp == kGemmWarps && lane == 0, 5);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::kTmemCols) : "memory");
   }
   if (world == 1) return;
 
-  // ====================================== phase 2: reduce the slices this rank owns =======================================
-  const int n_own = (n_tiles - rank + world - 1) / world;  // tiles rank, rank + world, ...
-  constexpr int kUnitsPerTile = BM / kUnitRows;
-  const int n_units = n_own * kUnitsPerTile;
-  const int64_t row_vecs = (int64_t)N / 8;  // 16-byte vectors per output row
-  int polled = -1;
-  // all flags of the unit's tile carry this call's epoch (">= e": a fast peer may already be in the next call)
-  auto wait_ready = [&](int tile) {
-    if (tile == polled) return;
-    if (warp == 0 && lane < world) {
-      const uint32_t* f = mine + kWReady + tile * world + lane;
-      while ((int32_t)(ld_acquire_sys(f) - e) < 0) {
-      }
-    }
-    __syncthreads();
-    polled = tile;
-  };
-  // unit u: 16 rows x 256 columns of an owned tile; warp w takes rows w and w + 8 of it, lane l the l-th 16 bytes
-  auto unit_addr = [&](int u, int half, bool& ok) -> uint4* {
-    const int tile = rank + (u / kUnitsPerTile) * world;
-    const int mt = tile % m_tiles, nt = tile / m_tiles;
-    const int r = mt * BM + (u % kUnitsPerTile) * kUnitRows + half * 8 + warp;
-    const int c = nt * BN + lane * 8;
-    ok = r < M && c < N;
-    return mc + (int64_t)r * row_vecs + (c >> 3);
-  };
-  int u = blockIdx.x;
-  uint4 cur[2], nxt[2];
-  bool okc[2], okn[2];
-  if (u < n_units) {
-    wait_ready(rank + (u / kUnitsPerTile) * world);
-    HG_OSTAMP(threadIdx.x == 0, 4);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint4* p = unit_addr(u, h, okc[h]);
-      if (okc[h]) cur[h] = mc_ld_reduce<T>(p);
-    }
-  }
-  while (u < n_units) {
-    const int u2 = u + gridDim.x;
-    if (u2 < n_units) {
-      wait_ready(rank + (u2 / kUnitsPerTile) * world);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint4* p = unit_addr(u2, h, okn[h]);
-        if (okn[h]) nxt[h] = mc_ld_reduce<T>(p);
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      bool ok;
-      uint4* p = unit_addr(u, h, ok);
-      if (ok) mc_st(p, cur[h]);
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      cur[h] = nxt[h];
-      okc[h] = okn[h];
-    }
-    u = u2;
-  }
-
   // ====================================== end: every slice of every rank has landed =======================================
-  __syncthreads();
-  HG_OSTAMP(threadIdx.x == 0, 5);
   if (threadIdx.x == 0) {
     __threadfence_system();  // this CTA's multicast stores are performed (acknowledged by every replica) before it is counted
     HG_OSTAMP(true, 6);
@@ -378,24 +404,64 @@ static int make_tmap(CUtensorMap* map, const void* base, int dtype, uint64_t row
   return HG_OK;
 }
 
+// HYDRAGEN_B200_OPROJ_BN = 128 | 256 (read once; development knob): output tile width.  Default: 128 when the product is
+// less than two waves of 256-wide tiles (so that tiles finish in at least two rounds and the reduction can start on the
+// first while the second is multiplied), else 256.
+static int oproj_bn_override() {
+  static const int v = [] {
+    const char* e = getenv("HYDRAGEN_B200_OPROJ_BN");
+    const int b = e != nullptr ? atoi(e) : 0;
+    return (b == 128 || b == 256) ? b : 0;
+  }();
+  return v;
+}
+// HYDRAGEN_B200_OPROJ_RWARPS = 1..8 (read once; development knob): reduce warps per CTA.  Each keeps 2 x kU 512-byte
+// reductions in flight; the switch path is saturated by about half a MiB in flight per GPU, and more than that only
+// delays the multicast stores behind a deeper queue of loads (r02za trace).
+static int oproj_reduce_warps() {
+  static const int v = [] {
+    const char* e = getenv("HYDRAGEN_B200_OPROJ_RWARPS");
+    const int w = e != nullptr ? atoi(e) : 2;
+    return (w >= 1 && w <= kMaxReduceWarps) ? w : 2;
+  }();
+  return v;
+}
+// HYDRAGEN_B200_OPROJ_SIGNAL (development knob): fence between a tile's bulk store and its flag: 0 none, 1 gpu scope
+// (default), 2 system scope.  Measured on 2 GPUs (r02zc, 40 checked rounds per variant): without a fence the switch
+// reads STALE tiles (14 bad rounds of 80); with the gpu-scope fence none, at +1 us; the system-scope one costs 5-8 us.
+static int oproj_signal_mode() {
+  static const int v = [] {
+    const char* e = getenv("HYDRAGEN_B200_OPROJ_SIGNAL");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  return v;
+}
+static int pick_bn(int64_t m, int64_t n, int world) {
+  if (oproj_bn_override() != 0) return oproj_bn_override();
+  const int n_sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int64_t wide = ((m + BM - 1) / BM) * ((n + 255) / 256);
+  return (world > 1 && wide < 2 * n_sms) ? 128 : 256;
+}
+
 int oproj_allreduce_flag_words(int64_t m, int64_t n, int world) {
-  const int64_t tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
+  const int64_t tiles = ((m + BM - 1) / BM) * ((n + 127) / 128);  // the narrow tiling: an upper bound for either
   return (int)(kWReady + tiles * world);
 }
 
-template <typename T>
+template <typename T, int BN>
 static int launch_inst(const OprojParams& p, cudaStream_t s) {
+  using C = Cfg<BN>;
   CUtensorMap tx, tw, to;
   int rc;
   if ((rc = make_tmap(&tx, p.x, p.dtype, (uint64_t)p.m, (uint64_t)p.k, (uint64_t)p.x_stride_row, BM)) != HG_OK) return rc;
   if ((rc = make_tmap(&tw, p.w, p.dtype, (uint64_t)p.n, (uint64_t)p.k, (uint64_t)p.w_stride_row, BN)) != HG_OK) return rc;
   if ((rc = make_tmap(&to, p.out, p.dtype, (uint64_t)p.m, (uint64_t)p.n, (uint64_t)p.n, BM)) != HG_OK) return rc;
-  auto kern = oproj_allreduce_sm100_kernel<T>;
+  auto kern = oproj_allreduce_sm100_kernel<T, BN>;
   static bool attr_set[64] = {};
   const int dev = device_info().device;
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return set_error(HG_ERR_CUDA, "oproj_allreduce: cannot reserve %d bytes of shared memory: %s", kSmemBytes, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return set_error(HG_ERR_CUDA, "oproj_allreduce: cannot reserve %d bytes of shared memory: %s", C::kSmemBytes, cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int n_sms = device_info().sm_count;
@@ -405,8 +471,8 @@ static int launch_inst(const OprojParams& p, cudaStream_t s) {
   if (p.n_ctas > 0) grid = std::min(p.n_ctas, n_sms);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.blockDim = dim3((unsigned)((kGemmWarps + (p.world > 1 ? oproj_reduce_warps() : 0)) * 32));
+  cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -414,7 +480,7 @@ static int launch_inst(const OprojParams& p, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tx, tw, to, reinterpret_cast<uint4*>(p.out_mc),
-                                     reinterpret_cast<uint32_t* const*>(p.flags_dev), p.rank, p.world, (int)p.m, (int)p.n, (int)p.k);
+                                     reinterpret_cast<uint32_t* const*>(p.flags_dev), p.rank, p.world, (int)p.m, (int)p.n, (int)p.k, oproj_signal_mode());
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(HG_ERR_CUDA, "oproj_allreduce: launch failed: %s", cudaGetErrorString(e));
@@ -423,8 +489,9 @@ static int launch_inst(const OprojParams& p, cudaStream_t s) {
 }
 
 int launch_oproj_allreduce(const OprojParams& p, cudaStream_t s) {
-  if (p.dtype == HG_BF16) return launch_inst<__nv_bfloat16>(p, s);
-  if (p.dtype == HG_F16) return launch_inst<__half>(p, s);
+  const int bn = pick_bn(p.m, p.n, p.world);
+  if (p.dtype == HG_BF16) return bn == 128 ? launch_inst<__nv_bfloat16, 128>(p, s) : launch_inst<__nv_bfloat16, 256>(p, s);
+  if (p.dtype == HG_F16) return bn == 128 ? launch_inst<__half, 128>(p, s) : launch_inst<__half, 256>(p, s);
   return set_error(HG_ERR_UNSUPPORTED, "oproj_allreduce: 16-bit types only (dtype %d)", p.dtype);
 }
 

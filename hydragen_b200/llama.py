@@ -106,6 +106,13 @@ class LlamaRMSNorm(nn.Module):
         return self.weight * xf.to(dt)
 
 
+def _rowwise_then_all_reduce(x: Tensor, lin: nn.Linear, all_reduce) -> Tensor:
+    """Row-parallel projection + the sum of its partials over the tensor-parallel group (hydragen/tp.py:99,108-112): one
+    fused launch where the collective offers it (tp._AllReduce.linear), else the two steps."""
+    fused = getattr(all_reduce, "linear", None)
+    return fused(x, lin) if fused is not None else all_reduce(lin(x))
+
+
 class LlamaMLP(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -115,10 +122,10 @@ class LlamaMLP(nn.Module):
         self.all_reduce = None  # set by tp.apply_tp
 
     def forward(self, x: Tensor) -> Tensor:
-        y = self.down_proj(nn.functional.silu(self.gate_proj(x)) * self.up_proj(x))
+        h = nn.functional.silu(self.gate_proj(x)) * self.up_proj(x)
         if self.all_reduce is not None:
-            y = self.all_reduce(y)
-        return y
+            return _rowwise_then_all_reduce(h, self.down_proj, self.all_reduce)
+        return self.down_proj(h)
 
 
 class HydragenLlamaRotaryEmbedding(nn.Module):
@@ -467,10 +474,10 @@ class HydragenLlamaAttention(nn.Module):
         else:
             raise ValueError(f"Unknown mode {self.mode}")
 
-        out = self.o_proj(out.reshape(b, s, self.num_heads * self.head_dim))
+        out = out.reshape(b, s, self.num_heads * self.head_dim)
         if self.all_reduce is not None:
-            out = self.all_reduce(out)
-        return out
+            return _rowwise_then_all_reduce(out, self.o_proj, self.all_reduce)
+        return self.o_proj(out)
 
 
 class HydragenLlamaDecoderLayer(nn.Module):

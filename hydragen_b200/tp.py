@@ -54,6 +54,9 @@ def shard_state_dict(sd: Dict[str, Tensor], rank: int, world_size: int) -> Dict[
     return out
 
 
+_FUSED_LINEAR = os.environ.get("HYDRAGEN_B200_FUSED_LINEAR", "1") != "0"  # 0: library GEMM, then the stand-alone collective
+
+
 class _AllReduce:
     """Sum over the tensor-parallel group on the compute stream.  Messages up to ``NVLS_MAX_BYTES`` (the decode-step
     ``[B, 1, hidden]`` sizes) go through the library's NVLS kernel (csrc/allreduce.cu) where the platform has NVLink
@@ -93,6 +96,31 @@ class _AllReduce:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
             _AllReduce._arenas[key] = entry if int(flag.item()) == 1 else None
         return _AllReduce._arenas[key]
+
+    def linear(self, x: Tensor, lin: nn.Linear) -> Tensor:
+        """all_reduce(lin(x)) for a row-parallel ``lin`` (o_proj: hydragen/llama.py:592-594 + hydragen/tp.py:108-112; the
+        MLP's down_proj alike).  Decode-sized 16-bit products run as ONE launch -- the tcgen05 GEMM whose tiles the NVSwitch
+        reduces as they are produced (csrc/oproj_allreduce.cu); everything else as the GEMM followed by ``__call__``."""
+        n, k = lin.weight.shape
+        m = x.numel() // max(k, 1)
+        nbytes = m * n * x.element_size()
+        if (self.use_nvls and _FUSED_LINEAR and x.is_cuda and lin.bias is None and x.dtype in (torch.bfloat16, torch.float16)
+                and lin.weight.dtype == x.dtype and m > 0 and 0 < nbytes <= self.NVLS_MAX_BYTES and n % 8 == 0 and k % 8 == 0
+                and dist.get_backend(self.group) == "nccl"):
+            entry = self._arena(x.device)
+            if entry is not None:
+                from . import _lib
+                from .collectives import GEMM_FLAG_WORDS
+
+                ar, halves, turn = entry
+                x2 = x.reshape(m, k)
+                if x2.stride(1) == 1 and x2.stride(0) % 8 == 0 and x2.data_ptr() % 16 == 0 and lin.weight.is_contiguous() \
+                        and _lib.oproj_allreduce_flag_words(m, n, ar.world) <= GEMM_FLAG_WORDS:
+                    buf = halves[turn][:nbytes].view(x.dtype).view(m, n)
+                    entry[2] = turn ^ 1
+                    ar.linear_all_reduce_(x2, lin.weight, buf)
+                    return buf.view(*x.shape[:-1], n)
+        return self(lin(x))
 
     def __call__(self, x: Tensor) -> Tensor:
         nbytes = x.numel() * x.element_size()

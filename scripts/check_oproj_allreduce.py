@@ -86,8 +86,26 @@ for m, n, kfull in shapes:
     for _ in range(3):
         fused()  # the same buffers again: partials overwrite the previous sums
     check("repeated")
+    # stress: many back-to-back eager rounds on the same buffers, checked after each (a stale read of a partial shows as the
+    # previous sum leaking into the new one)
+    bad = 0
+    for it in range(int(os.environ.get("OPROJ_STRESS", "0"))):
+        fused()
+        torch.cuda.synchronize()
+        err = max((b.float() - r).abs().max().item() for b, r in zip(bufs, refs))
+        bad += int(not err <= scale / 64)
+    if os.environ.get("OPROJ_STRESS"):
+        t = torch.tensor([bad], device=dev)
+        dist.all_reduce(t)
+        ok = ok and int(t.item()) == 0
+        if rank == 0:
+            print(f"  [{m},{n}] stress: {int(t.item())} bad rounds (summed over ranks) of {os.environ['OPROJ_STRESS']}", flush=True)
     t_fused = timed(fused)
     check("graph replay")
+    if os.environ.get("OPROJ_FUSED_ONLY"):
+        if rank == 0:
+            print(f"world {world} [{m},{n}] k={k}/rank, us per o_proj + all-reduce: fused {t_fused:.1f}", flush=True)
+        continue
 
     def lib_nvls():
         for x, w, b in zip(xs, ws, bufs):

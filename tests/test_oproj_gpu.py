@@ -1,10 +1,15 @@
 """The tcgen05 GEMM of csrc/oproj_allreduce.cu on one GPU (world == 1: no collective): out = x @ w.T against a torch fp32
 reference of the same op (hydragen/llama.py:592-594, o_proj on the local heads).  The multi-rank form is covered by
 tests/test_multigpu_gpu.py (torchrun)."""
+import os
+import subprocess
+import sys
+
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _run(m, n, k, dtype, x_stride=None, n_ctas=0, seed=0):
@@ -58,3 +63,12 @@ def test_rejects_bad_arguments():
         _lib.oproj_allreduce_fwd(x.float(), w.float(), torch.zeros(16, 32, device="cuda"))
     with pytest.raises(RuntimeError):  # k not a multiple of 8
         _lib.oproj_allreduce_fwd(x[:, :20], w[:, :20], torch.zeros(16, 32, device="cuda", dtype=torch.bfloat16))
+
+
+@pytest.mark.skipif(os.environ.get("HYDRAGEN_B200_OPROJ_BN") is not None, reason="already the narrow-tile run")
+def test_narrow_tiles():
+    """The 128-column tiling (what multi-rank launches of one-wave products use; a per-process switch) on the same cases."""
+    env = dict(os.environ, HYDRAGEN_B200_OPROJ_BN="128")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", os.path.abspath(__file__), "-k",
+                        "gemm_matches or strided"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0 and " passed" in r.stdout, (r.stdout + r.stderr)[-3000:]
