@@ -23,6 +23,7 @@ lightest point of a decode (suffix 1); the projections / MLP / sampling around i
   `full_model`         configs[2] itself: random-init Llama-2-7B generate(1024 x 128 tokens), whole-model tokens/s;
   `sustained`          the same step replayed for seconds, against the sustained cuBLAS peak, with clocks;
   `lib_fa2`            the installed flash-attn 2.x kernels on the same tensors (the library the reference calls);
+  `oproj_allreduce`    N > 1: the o_proj GEMM + all-reduce pair per layer, library GEMM + NVLS kernel vs ONE fused launch, alone and in the step;
   `hierarchy_cfg4`     configs[3]: the two-level hierarchy 1 x 1024 -> 32 x 64 -> B = 1024, one grouped prefix launch per layer.
 
 Multi-GPU = the reference's head-axis tensor parallelism (hydragen/tp.py): each rank runs the same
@@ -647,6 +648,55 @@ def run_ours(a):
         except Exception as ex:
             hierarchy = {"error": repr(ex)[:300]}
 
+    # ---- the row-parallel o_proj GEMM + the all-reduce of its partials, per layer, as the library GEMM followed
+    # by the stand-alone NVLS kernel (what `value` above contains is the collective alone) and as ONE fused launch
+    # (csrc/oproj_allreduce.cu) -- the pair on its own and inside the step (attention -> o_proj -> all-reduce) ----------
+    oproj = None
+    if world > 1 and nvls is not None and not a.no_sweep:
+        try:
+            kloc = H * D
+            ws = [torch.randn(hidden, kloc, device=dev, dtype=dt) / hidden**0.5 for _ in range(L)]
+            xv = [torch.randn(B, kloc, device=dev, dtype=dt) for _ in range(L)]
+
+            def attn(i):
+                return hydragen_attention_decode(qs[i], kn[i], vn[i], pos, uniq[i, 0], uniq[i, 1], [shared_k[i]], [shared_v[i]]).view(B, kloc)
+
+            def pair_fused():
+                for i in range(L):
+                    nvls.linear_all_reduce_(xv[i], ws[i], proj[i])
+
+            def pair_lib():
+                for i in range(L):
+                    torch.matmul(xv[i], ws[i].t(), out=proj[i])
+                    nvls.all_reduce_(proj[i])
+
+            def step_fused():
+                for i in range(L):
+                    nvls.linear_all_reduce_(attn(i), ws[i], proj[i])
+
+            def step_lib():
+                for i in range(L):
+                    torch.matmul(attn(i), ws[i].t(), out=proj[i])
+                    nvls.all_reduce_(proj[i])
+
+            def timed_multi(fn, launches):
+                g = make_graph(fn)
+                barrier()
+                us, _ = time_graph(g, launches)
+                del g
+                return max_over_ranks(us)
+
+            pf, pl = timed_multi(pair_fused, L), timed_multi(pair_lib, L)
+            sf, sl = timed_multi(step_fused, 1) / 1e3, timed_multi(step_lib, 1) / 1e3
+            oproj = {"what": f"per layer: o_proj [B={B}, {kloc}] x [{hidden}, {kloc}]^T (this rank's heads) + all-reduce of the [B, {hidden}] bf16 partials "
+                             "(hydragen/llama.py:592-594 + tp.py:108-112); graph-timed, max over ranks",
+                     "pair_us": {"fused_tcgen05_gemm_nvls": pf, "cublas_then_nvls_kernel": pl},
+                     "step_ms": {"attention_then_fused": sf, "attention_then_cublas_then_nvls_kernel": sl},
+                     "tokens_per_s": {"attention_then_fused": B / (sf / 1e3), "attention_then_cublas_then_nvls_kernel": B / (sl / 1e3)}}
+            del ws, xv
+        except Exception as ex:
+            oproj = {"error": repr(ex)[:300]}
+
     used_graph = graph is not None
     full_model = None
     if world == 1 and not a.no_full_model:
@@ -675,7 +725,7 @@ def run_ours(a):
             "roofline": roofline, "roofline_suffix": roofline_suffix, "roofline_rope": roofline_rope, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
             "sustained": sustained, "suffix_sweep": suffix_sweep, "decode_integrated": decode_integrated, "lib_fa2": lib_fa2,
-            "hierarchy_cfg4": hierarchy,
+            "hierarchy_cfg4": hierarchy, "oproj_allreduce": oproj,
         }
         if full_model is not None:
             line["full_model"] = full_model

@@ -3,15 +3,17 @@
 // funcol.all_reduce in hydragen/tp.py:108-112 -- as ONE persistent kernel per rank:
 //
 //   phase 1 (tcgen05)  out_partial[m, n] = sum_k x[m, k] * w[n, k]   x = local attention output [M, K] (K = local heads * d),
-//                      w = this rank's column slice of o_proj.weight [N, K], both K-major.  128 x 256 output tiles,
-//                      64-wide k-blocks through a 3-deep TMA ring, fp32 accumulators double-buffered in TMEM (2 x 256
-//                      columns), epilogue TMEM -> bf16 -> swizzled smem -> TMA store into this rank's SYMMETRIC buffer.
-//                      When a tile's store has completed, its producer raises one flag word in the memory of the rank
-//                      that OWNS the tile (tile % world): "rank r's partial of tile t, call e, is in place".
-//   phase 2 (NVLS)     every CTA then walks the 16-row slices of the tiles this rank owns: wait until all `world` flags
-//                      of the slice's tile carry the call's epoch, multimem.ld_reduce the slice (the switch fetches it from
-//                      every rank and adds in fp32), multimem.st the sum into every rank's buffer.  The next slice's
-//                      reductions are issued before the current slice's stores (the two load opposite link directions).
+//                      w = this rank's column slice of o_proj.weight [N, K], both K-major.  128 x 128 output tiles (128 x 256
+//                      for the GEMM alone), 64-wide k-blocks through a 5- (3-) deep TMA ring, fp32 accumulators double-buffered
+//                      in TMEM, epilogue TMEM -> 16-bit -> swizzled smem -> TMA store into this rank's SYMMETRIC buffer.
+//                      When a tile's store has completed and a gpu-scope fence has passed, its producer raises one flag word in
+//                      the memory of the rank that OWNS the tile (tile % world): "rank r's partial of tile t, call e, is in place".
+//                      Warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer.
+//   phase 2 (NVLS)     runs BESIDE phase 1 on 2-4 more warps per CTA, each on its own: walk slices (a few rows) of the tiles
+//                      this rank owns, in the order the tiles are produced; wait until all `world` flags of the slice's tile
+//                      carry the call's epoch, multimem.ld_reduce the slice (the switch fetches it from every rank and adds in
+//                      fp32), multimem.st the sum into every rank's buffer.  The next slice's reductions are issued before
+//                      the current slice's stores (the two load opposite link directions).
 //   end                the CTAs count themselves out; the last one tells every peer "my slices are written everywhere",
 //                      waits for the same from them, and bumps the epoch -- the grid retires only when `out` is complete.
 //
@@ -43,11 +45,11 @@ constexpr int kMaxReduceWarps = 8;  // warps 6...: phase 2, running beside phase
 constexpr int kThreads = (kGemmWarps + kMaxReduceWarps) * 32;
 constexpr int kABytes = BM * BK * 2;    // one TMA box: 128 rows x 128 B
 constexpr int kBoxBytes = BM * 64 * 2;  // one output box: 128 rows x 64 columns
-constexpr int kU = 4;                   // reductions in flight per lane and slice (and as many again prefetched)
 
 // BN = 256: three 48 KiB ring slots; BN = 128: five 32 KiB slots.  Narrow tiles cost a third more operand traffic but
 // finish in more, shorter waves -- which is what lets the reduction start early when the whole product is one wave wide.
-template <int BN>
+// U = reductions in flight per lane and slice (and as many again prefetched)
+template <int BN, int U>
 struct Cfg {
   static constexpr int kStages = BN == 256 ? 3 : 5;
   static constexpr int kBBytes = BN * BK * 2;  // one TMA box: BN rows x 128 B
@@ -59,7 +61,7 @@ struct Cfg {
   static constexpr uint32_t kTmemCols = 2 * BN;             // two 128 x BN fp32 accumulators
   static constexpr int kLanesPerRow = BN / 8;               // 16-byte vectors in a tile row
   static constexpr int kRowsPerInst = 32 / kLanesPerRow;    // tile rows one warp-wide reduction covers
-  static constexpr int kUnitRows = kU * kRowsPerInst;       // rows of a tile one warp reduces at a time
+  static constexpr int kUnitRows = U * kRowsPerInst;       // rows of a tile one warp reduces at a time
   static constexpr int kUnitsPerTile = BM / kUnitRows;
 };
 constexpr int kMaxStages = 5;
@@ -137,12 +139,12 @@ __device__ __forceinline__ void op_stamp(int stage) {
 
 }  // namespace
 
-template <typename T, int BN>
+template <typename T, int BN, int kU>
 __global__ void __launch_bounds__(kThreads, 1)
     oproj_allreduce_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                                  const __grid_constant__ CUtensorMap tmap_out, uint4* __restrict__ mc,
                                  uint32_t* const* __restrict__ flags, int rank, int world, int M, int N, int K, int signal_mode) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, kU>;
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t kIdesc = make_idesc(kFmt, 0, BM, BN);
   extern __shared__ uint8_t smem_raw[];
@@ -404,43 +406,40 @@ static int make_tmap(CUtensorMap* map, const void* base, int dtype, uint64_t row
   return HG_OK;
 }
 
-// HYDRAGEN_B200_OPROJ_BN = 128 | 256 (read once; development knob): output tile width.  Default: 128 when the product is
-// less than two waves of 256-wide tiles (so that tiles finish in at least two rounds and the reduction can start on the
-// first while the second is multiplied), else 256.
-static int oproj_bn_override() {
-  static const int v = [] {
-    const char* e = getenv("HYDRAGEN_B200_OPROJ_BN");
-    const int b = e != nullptr ? atoi(e) : 0;
-    return (b == 128 || b == 256) ? b : 0;
-  }();
-  return v;
+// Development knobs, read at every launch (so that one process can sweep them; a captured graph keeps what it was captured with):
+//   HYDRAGEN_B200_OPROJ_BN = 128 | 256   output tile width.  Default: 128 whenever there is a collective (tiles finish in more,
+//                                        shorter rounds, so the reduction of the first overlaps the multiplication of the rest:
+//                                        r02zf / r02zg, 3-13 % faster than 256 on 2 and on 8 GPUs), 256 for the GEMM alone
+//   HYDRAGEN_B200_OPROJ_RWARPS = 1..8    reduce warps per CTA
+//   HYDRAGEN_B200_OPROJ_U = 1 | 2 | 4    reductions per lane and slice; a warp has 2 U x 512 bytes in flight.  What matters is the
+//                                        product CTAs x warps x 2 U = bytes of OUTPUT in flight per GPU, each of which the switch
+//                                        assembles from `world` reads: enough to cover the round trip, not so much that the
+//                                        multicast stores -- which load the OPPOSITE link direction -- only start when the queue of
+//                                        reductions has drained.  Measured optimum (r02zf, r02zg): ~2.3 MiB on 2 GPUs, ~0.6 MiB on 8
+//                                        (148 KiB: latency-bound, 1.5-3.5x slower); the default follows 4.6 MiB / world
+//   HYDRAGEN_B200_OPROJ_SIGNAL = 0|1|2   fence between a tile's bulk store and its flag: none / gpu scope (default) / system scope.
+//                                        Measured on 2 GPUs (r02zc, 40 checked rounds per variant): without a fence the switch reads
+//                                        STALE tiles (14 bad rounds of 80); with the gpu-scope fence none, at +1 us; system scope
+//                                        costs 5-8 us
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
 }
-// HYDRAGEN_B200_OPROJ_RWARPS = 1..8 (read once; development knob): reduce warps per CTA.  Each keeps 2 x kU 512-byte
-// reductions in flight; the switch path is saturated by about half a MiB in flight per GPU, and more than that only
-// delays the multicast stores behind a deeper queue of loads (r02za trace).
-static int oproj_reduce_warps() {
-  static const int v = [] {
-    const char* e = getenv("HYDRAGEN_B200_OPROJ_RWARPS");
-    const int w = e != nullptr ? atoi(e) : 2;
-    return (w >= 1 && w <= kMaxReduceWarps) ? w : 2;
-  }();
-  return v;
+static int oproj_signal_mode() { return env_int("HYDRAGEN_B200_OPROJ_SIGNAL", 1); }
+static int oproj_reduce_warps(int world) {
+  const int w = env_int("HYDRAGEN_B200_OPROJ_RWARPS", 0);
+  return (w >= 1 && w <= kMaxReduceWarps) ? w : (world <= 2 ? 4 : 2);
 }
-// HYDRAGEN_B200_OPROJ_SIGNAL (development knob): fence between a tile's bulk store and its flag: 0 none, 1 gpu scope
-// (default), 2 system scope.  Measured on 2 GPUs (r02zc, 40 checked rounds per variant): without a fence the switch
-// reads STALE tiles (14 bad rounds of 80); with the gpu-scope fence none, at +1 us; the system-scope one costs 5-8 us.
-static int oproj_signal_mode() {
-  static const int v = [] {
-    const char* e = getenv("HYDRAGEN_B200_OPROJ_SIGNAL");
-    return e != nullptr ? atoi(e) : 1;
-  }();
-  return v;
+static int oproj_u(int world) {
+  const int u = env_int("HYDRAGEN_B200_OPROJ_U", 0);
+  return (u == 1 || u == 2 || u == 4) ? u : (world <= 4 ? 4 : 2);
 }
 static int pick_bn(int64_t m, int64_t n, int world) {
-  if (oproj_bn_override() != 0) return oproj_bn_override();
-  const int n_sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
-  const int64_t wide = ((m + BM - 1) / BM) * ((n + 255) / 256);
-  return (world > 1 && wide < 2 * n_sms) ? 128 : 256;
+  const int b = env_int("HYDRAGEN_B200_OPROJ_BN", 0);
+  if (b == 128 || b == 256) return b;
+  (void)m;
+  (void)n;
+  return world > 1 ? 128 : 256;
 }
 
 int oproj_allreduce_flag_words(int64_t m, int64_t n, int world) {
@@ -448,15 +447,15 @@ int oproj_allreduce_flag_words(int64_t m, int64_t n, int world) {
   return (int)(kWReady + tiles * world);
 }
 
-template <typename T, int BN>
+template <typename T, int BN, int U>
 static int launch_inst(const OprojParams& p, cudaStream_t s) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, U>;
   CUtensorMap tx, tw, to;
   int rc;
   if ((rc = make_tmap(&tx, p.x, p.dtype, (uint64_t)p.m, (uint64_t)p.k, (uint64_t)p.x_stride_row, BM)) != HG_OK) return rc;
   if ((rc = make_tmap(&tw, p.w, p.dtype, (uint64_t)p.n, (uint64_t)p.k, (uint64_t)p.w_stride_row, BN)) != HG_OK) return rc;
   if ((rc = make_tmap(&to, p.out, p.dtype, (uint64_t)p.m, (uint64_t)p.n, (uint64_t)p.n, BM)) != HG_OK) return rc;
-  auto kern = oproj_allreduce_sm100_kernel<T, BN>;
+  auto kern = oproj_allreduce_sm100_kernel<T, BN, U>;
   static bool attr_set[64] = {};
   const int dev = device_info().device;
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -471,7 +470,7 @@ static int launch_inst(const OprojParams& p, cudaStream_t s) {
   if (p.n_ctas > 0) grid = std::min(p.n_ctas, n_sms);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)((kGemmWarps + (p.world > 1 ? oproj_reduce_warps() : 0)) * 32));
+  cfg.blockDim = dim3((unsigned)((kGemmWarps + (p.world > 1 ? oproj_reduce_warps(p.world) : 0)) * 32));
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -488,10 +487,22 @@ static int launch_inst(const OprojParams& p, cudaStream_t s) {
   return check_launch("oproj_allreduce");
 }
 
+template <typename T>
+static int launch_type(const OprojParams& p, cudaStream_t s) {
+  const int bn = pick_bn(p.m, p.n, p.world), u = p.world > 1 ? oproj_u(p.world) : 4;
+  if (bn == 128) {
+    if (u == 1) return launch_inst<T, 128, 1>(p, s);
+    if (u == 2) return launch_inst<T, 128, 2>(p, s);
+    return launch_inst<T, 128, 4>(p, s);
+  }
+  if (u == 1) return launch_inst<T, 256, 1>(p, s);
+  if (u == 2) return launch_inst<T, 256, 2>(p, s);
+  return launch_inst<T, 256, 4>(p, s);
+}
+
 int launch_oproj_allreduce(const OprojParams& p, cudaStream_t s) {
-  const int bn = pick_bn(p.m, p.n, p.world);
-  if (p.dtype == HG_BF16) return bn == 128 ? launch_inst<__nv_bfloat16, 128>(p, s) : launch_inst<__nv_bfloat16, 256>(p, s);
-  if (p.dtype == HG_F16) return bn == 128 ? launch_inst<__half, 128>(p, s) : launch_inst<__half, 256>(p, s);
+  if (p.dtype == HG_BF16) return launch_type<__nv_bfloat16>(p, s);
+  if (p.dtype == HG_F16) return launch_type<__half>(p, s);
   return set_error(HG_ERR_UNSUPPORTED, "oproj_allreduce: 16-bit types only (dtype %d)", p.dtype);
 }
 
