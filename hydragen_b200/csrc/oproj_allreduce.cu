@@ -154,6 +154,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int m_tiles = (M + BM - 1) / BM, n_tiles = m_tiles * ((N + BN - 1) / BN), n_kb = (K + BK - 1) / BK;
 
   HG_OSTAMP(threadIdx.x == 0, 0);
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::kStages; ++i) {
       mbar_init(&bars->full[i], 1);
@@ -234,7 +239,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_after();
       HG_OSTAMP(threadIdx.x == 0 && lt == 0, 2);
       const uint32_t t_addr = tmem + (uint32_t)acc * BN + ((uint32_t)(warp * 32) << 16);
-      // accumulator -> 16-bit -> the TMA 128-byte swizzle: row r keeps 16-byte chunk c of a 64-column box at slot c ^ (r & 7)
+      // accumulator -> 16-bit -> the TMA 128-byte swizzle: row r keeps 16-byte chunk c of a 64-column box at slot c ^ (r & 7).
+      // (Storing straight from the registers -- one row per lane, every thread fencing its own stores -- was measured instead,
+      // r02zi: the flag leaves 1.5 us LATER and the pair is 1.5-3 us slower; the bulk store is the fast way out.)
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t o[32];
