@@ -121,6 +121,31 @@ def test_new_entry_points_validate_without_gpu(built_lib):
     assert rc == -4
 
 
+def test_oproj_allreduce_validates_without_gpu(built_lib):
+    """hg_oproj_allreduce_fwd rejects bad arguments before any CUDA call; the flag-word count is a host-side formula."""
+    from hydragen_b200 import _lib
+
+    lib = _lib.load()
+    # 128 header words + (128-row x 128-column tiles) x world
+    assert lib.hg_oproj_allreduce_flag_words(1024, 4096, 8) == 128 + 8 * 32 * 8
+    assert lib.hg_oproj_allreduce_flag_words(1, 8, 2) == 128 + 2
+    assert lib.hg_oproj_allreduce_flag_words(-1, 8, 2) == 0
+    buf = ctypes.c_void_p(4096)
+    call = lambda **kw: lib.hg_oproj_allreduce_fwd(  # noqa: E731
+        kw.get("x", buf), kw.get("xs", 512), kw.get("w", buf), kw.get("ws", 512), kw.get("out", buf), kw.get("mc", buf), kw.get("flags", buf),
+        kw.get("words", 1 << 20), kw.get("rank", 0), kw.get("world", 2), kw.get("m", 1024), kw.get("n", 4096), kw.get("k", 512), kw.get("dtype", 1),
+        kw.get("ctas", 0), None)
+    assert call(dtype=2) == -2 and b"16-bit" in lib.hg_last_error()  # fp32 is not a tensor-core input type here
+    assert call(rank=2) == -1 and b"rank" in lib.hg_last_error()
+    assert call(k=508) == -2 and b"multiples of 8" in lib.hg_last_error()
+    assert call(xs=256) == -2  # row stride smaller than k
+    assert call(mc=None) == -1 and b"multicast" in lib.hg_last_error()
+    assert call(words=64) == -1 and b"flag words" in lib.hg_last_error()
+    assert call(m=0) == -1 and b"empty" in lib.hg_last_error()  # a rank may not skip a collective call
+    assert call(x=None) == -1 and b"null" in lib.hg_last_error()
+    assert call(world=1, m=0) == 0  # the GEMM alone on nothing: a no-op
+
+
 def test_rope_and_causal_refuse_cpu_tensors():
     from hydragen_b200._lib import HydragenB200Error
     from hydragen_b200.flash import flash_attention
