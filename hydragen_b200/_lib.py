@@ -80,6 +80,7 @@ SYMBOLS = {
          c_int, c_void_p],
     ),
     "hg_oproj_allreduce_flag_words": (c_int, [c_int64, c_int64, c_int]),
+    "hg_oproj_allreduce_plan": (c_int, [c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hg_kv_append": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
@@ -324,6 +325,17 @@ def allreduce_multimem(mc_ptr: int, out_ptr: int, flags_dev: int, rank: int, wor
 
 def oproj_allreduce_flag_words(m: int, n: int, world: int) -> int:
     return int(load().hg_oproj_allreduce_flag_words(m, n, world))
+
+
+def oproj_allreduce_plan(m: int, n: int, world: int, rank: int, n_ctas: int = 0, cover=None) -> dict:
+    """Host-side view of the fused o_proj + all-reduce launch (hg_oproj_allreduce_plan; no device work).  ``cover``: a zeroed
+    int32 numpy array of m * n / 8 entries that receives how often ``rank`` reduces each 16-byte vector of the output."""
+    geo = (c_int * 8)()
+    rc = load().hg_oproj_allreduce_plan(m, n, world, rank, n_ctas, ctypes.cast(geo, c_void_p),
+                                        c_void_p(cover.ctypes.data) if cover is not None else None)
+    _check(rc, "hg_oproj_allreduce_plan")
+    keys = ("bn", "u", "reduce_warps", "ctas", "tiles", "tiles_owned", "slices_owned", "flag_words")
+    return dict(zip(keys, list(geo)))
 
 
 def oproj_allreduce_fwd(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, out_mc: int = 0, flags_dev: int = 0, flag_words: int = 0,

@@ -21,7 +21,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 OUT_DIR = os.path.join(PKG_DIR, "_C")
 LIB_PATH = os.path.join(OUT_DIR, "libhydragen_b200.so")
 SOURCES = ["api.cu", "combine.cu", "rowwise.cu", "prefix_sm100.cu", "prefix_unit_sm100.cu", "prefix_unit_sm100_causal.cu", "allreduce.cu", "oproj_allreduce.cu", "rope.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "prefix_sched.h"), os.path.join(CSRC, "sm100_ptx.cuh"), os.path.join(ROOT, "include", "hydragen_b200.h")]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "prefix_sched.h"), os.path.join(CSRC, "oproj_sched.h"), os.path.join(CSRC, "sm100_ptx.cuh"), os.path.join(ROOT, "include", "hydragen_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -361,6 +361,12 @@ int hg_oproj_allreduce_flag_words(int64_t m, int64_t n, int world) {
   return oproj_allreduce_flag_words(m, n, world);
 }
 
+int hg_oproj_allreduce_plan(int64_t m, int64_t n, int world, int rank, int n_ctas, int* geometry_out, int32_t* cover_out) {
+  if (m < 1 || n < 8 || n % 8 != 0 || m > INT32_MAX || n > INT32_MAX || world < 1 || world > 32 || rank < 0 || rank >= world || n_ctas < 0)
+    return set_error(HG_ERR_INVALID_ARGUMENT, "oproj_allreduce_plan: bad arguments");
+  return oproj_allreduce_plan(m, n, world, rank, n_ctas, geometry_out, cover_out);
+}
+
 int hg_oproj_allreduce_fwd(const void* x, int64_t x_stride_row, const void* w, int64_t w_stride_row, void* out, void* out_mc,
                            const void* flags_dev, int64_t flag_words, int rank, int world, int64_t m, int64_t n, int64_t k, int dtype,
                            int n_ctas, void* stream) {

@@ -208,6 +208,7 @@ struct OprojParams {
 };
 int launch_oproj_allreduce(const OprojParams& p, cudaStream_t s);
 int oproj_allreduce_flag_words(int64_t m, int64_t n, int world);
+int oproj_allreduce_plan(int64_t m, int64_t n, int world, int rank, int n_ctas, int* geometry_out, int32_t* cover_out);
 
 int launch_kv_append(const void* k_new, const void* v_new, const void* positions, int positions_i64, void* k_cache,
                      void* v_cache, int b, int nq, int lk, int hkv, int d, int dtype, cudaStream_t s);

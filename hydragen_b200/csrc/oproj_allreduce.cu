@@ -33,13 +33,14 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "oproj_sched.h"
 #include "sm100_ptx.cuh"
 
 namespace hg {
 
 namespace {
 
-constexpr int BM = 128, BK = 64;
+constexpr int BM = kOprojBM, BK = 64;
 constexpr int kGemmWarps = 6;    // warps 0-3 epilogue (TMEM lane quarter = warp), 4 TMA, 5 MMA
 constexpr int kMaxReduceWarps = 8;  // warps 6...: phase 2, running beside phase 1 (how many is a launch parameter)
 constexpr int kThreads = (kGemmWarps + kMaxReduceWarps) * 32;
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         asm volatile("fence.proxy.async.global;" ::: "memory");
         if (signal_mode == 1) __threadfence();
         if (signal_mode == 2) __threadfence_system();
-        st_relaxed_sys(flags[tile % world] + kWReady + tile * world + rank, e);
+        st_relaxed_sys(flags[oproj_owner(tile, world)] + kWReady + tile * world + rank, e);
         HG_OSTAMP(lt == 0, 8);
       }
     }
@@ -294,10 +295,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     // multiplied.  Each warp is on its own -- no CTA-wide barrier: lanes < world poll the tile's flags, the warp converges,
     // then every lane keeps kU reductions in flight and issues the next slice's before it multicasts this one's (the two
     // load opposite link directions).
-    const int n_own = (n_tiles - rank + world - 1) / world;  // tiles rank, rank + world, ...
-    const int n_units = n_own * C::kUnitsPerTile;
+    const OprojGeom geo = oproj_geom(M, N, BN, kU, world, rank);  // who reduces what: oproj_sched.h
+    const int n_units = geo.n_units;
     const int64_t row_vecs = (int64_t)N / 8;  // 16-byte vectors per output row
-    const int stride = gridDim.x * ((int)(blockDim.x >> 5) - kGemmWarps);
+    const int stride = oproj_unit_stride(gridDim.x, (int)(blockDim.x >> 5) - kGemmWarps);
     int polled = -1;
     // all flags of the slice's tile carry this call's epoch (">= e": a fast peer may already be in the next call)
     auto wait_ready = [&](int tile) {
@@ -309,20 +310,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
       polled = tile;
     };
-    // slice u: kUnitRows rows x BN columns of an owned tile; instruction j of the warp covers kRowsPerInst of its rows
+    // slice u: unit_rows rows x BN columns of an owned tile; instruction j of the warp covers rows_per_inst of its rows
     auto unit_addr = [&](int u, int j, bool& ok) -> uint4* {
-      const int tile = rank + (u / C::kUnitsPerTile) * world;
-      const int mt = tile % m_tiles, nt = tile / m_tiles;
-      const int r = mt * BM + (u % C::kUnitsPerTile) * C::kUnitRows + j * C::kRowsPerInst + lane / C::kLanesPerRow;
-      const int c = nt * BN + (lane % C::kLanesPerRow) * 8;
-      ok = r < M && c < N;
+      int r, c;
+      ok = oproj_unit_vector(geo, u, j, lane, &r, &c);
       return mc + (int64_t)r * row_vecs + (c >> 3);
     };
     // warp w of CTA b starts at slice w * gridDim.x + b: the slices of the earliest tiles are spread over all SMs
-    int u = (warp - kGemmWarps) * gridDim.x + blockIdx.x;
+    int u = oproj_first_unit(blockIdx.x, warp - kGemmWarps, gridDim.x);
     uint4 cur[kU], nxt[kU];
     if (u < n_units) {
-      wait_ready(rank + (u / C::kUnitsPerTile) * world);
+      wait_ready(oproj_unit_tile(geo, u));
       HG_OSTAMP(warp == kGemmWarps && lane == 0, 4);
 #pragma unroll
       for (int j = 0; j < kU; ++j) {
@@ -334,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     while (u < n_units) {
       const int u2 = u + stride;
       if (u2 < n_units) {
-        wait_ready(rank + (u2 / C::kUnitsPerTile) * world);
+        wait_ready(oproj_unit_tile(geo, u2));
 #pragma unroll
         for (int j = 0; j < kU; ++j) {
           bool ok;
@@ -452,6 +450,33 @@ static int pick_bn(int64_t m, int64_t n, int world) {
 int oproj_allreduce_flag_words(int64_t m, int64_t n, int world) {
   const int64_t tiles = ((m + BM - 1) / BM) * ((n + 127) / 128);  // the narrow tiling: an upper bound for either
   return (int)(kWReady + tiles * world);
+}
+
+// Host-side view of a launch (hg_oproj_allreduce_plan): the geometry launch_oproj_allreduce would choose for this shape
+// and, replayed from the device formulas, how often each 16-byte vector of the output is reduced by rank `rank`.
+int oproj_allreduce_plan(int64_t m, int64_t n, int world, int rank, int n_ctas, int* geometry_out, int32_t* cover_out) {
+  const int n_sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int bn = pick_bn(m, n, world), u = world > 1 ? oproj_u(world) : 4, warps = world > 1 ? oproj_reduce_warps(world) : 0;
+  const int64_t n_tiles = ((m + BM - 1) / BM) * ((n + bn - 1) / bn);
+  int grid = world > 1 ? n_sms : (int)std::min<int64_t>(n_tiles, n_sms);
+  if (n_ctas > 0) grid = std::min(n_ctas, n_sms);
+  const OprojGeom g = oproj_geom((int)m, (int)n, bn, u, world, rank);
+  if (geometry_out != nullptr) {
+    const int v[8] = {bn, u, warps, grid, g.n_tiles, g.n_own, g.n_units, kWReady + g.n_tiles * world};
+    for (int i = 0; i < 8; ++i) geometry_out[i] = v[i];
+  }
+  if (cover_out != nullptr && world > 1) {
+    const int stride = oproj_unit_stride(grid, warps);
+    for (int cta = 0; cta < grid; ++cta)
+      for (int w = 0; w < warps; ++w)
+        for (int unit = oproj_first_unit(cta, w, grid); unit < g.n_units; unit += stride)
+          for (int j = 0; j < u; ++j)
+            for (int lane = 0; lane < 32; ++lane) {
+              int r, c;
+              if (oproj_unit_vector(g, unit, j, lane, &r, &c)) cover_out[(int64_t)r * (n / 8) + c / 8] += 1;
+            }
+  }
+  return HG_OK;
 }
 
 template <typename T, int BN, int U>

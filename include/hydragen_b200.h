@@ -292,6 +292,13 @@ int hg_oproj_allreduce_fwd(const void* x, int64_t x_stride_row, const void* w, i
                            void* out_mc, const void* flags_dev, int64_t flag_words, int rank, int world, int64_t m,
                            int64_t n, int64_t k, int dtype, int n_ctas, void* stream);
 int hg_oproj_allreduce_flag_words(int64_t m, int64_t n, int world);
+/* Host-side view of that launch, for tests and tooling (no device work): the geometry hg_oproj_allreduce_fwd would use --
+ * geometry_out[8] = {tile width, reductions per lane and slice, reduce warps per CTA, CTAs, tiles of the product, tiles and
+ * slices rank `rank` owns, flag words needed} -- and, if cover_out != NULL (m * n / 8 int32, caller-zeroed), how many times
+ * rank `rank` reduces each 16-byte vector of the [m, n] output (added into cover_out: summed over the ranks it must be 1
+ * everywhere). */
+int hg_oproj_allreduce_plan(int64_t m, int64_t n, int world, int rank, int n_ctas, int* geometry_out,
+                            int32_t* cover_out);
 
 /* ---------------------------------------------------------------------------------------
  * Rotary position embedding of the new q and k rows in one launch ("next" row N2 of SURVEY.md 8f): the
