@@ -36,16 +36,19 @@ def timed(fn, reps=20):
     return e0.elapsed_time(e1) * 1e3 / (reps * L)
 
 
-for suffix in (1, 2, 16, 64):
+for suffix, rows in ((1, LK), (1, 32), (1, 1), (2, LK), (2, 32), (16, LK), (16, 32), (16, 16), (64, LK)):
     pos = torch.full((B, 1), suffix - 1, device=dev, dtype=torch.int64)
+    # `rows`: how many rows of the 128-row caches the call is shown (a view; <= 32 selects the short-cache variant of the kernel)
+    kc = [uniq[i, 0][:, :rows] for i in range(L)]
+    vc = [uniq[i, 1][:, :rows] for i in range(L)]
 
     def only_suffix():
         for i in range(L):
-            decode_attention_fused(qs[i], kn[i], vn[i], pos, uniq[i, 0], uniq[i, 1], pre[i][0], pre[i][1])
+            decode_attention_fused(qs[i], kn[i], vn[i], pos, kc[i], vc[i], pre[i][0], pre[i][1])
 
     def step():
         for i in range(L):
             o, l = prefix_attention_partials(qs[i], sk[i], sv[i], 1, max_splits=1)
-            decode_attention_fused(qs[i], kn[i], vn[i], pos, uniq[i, 0], uniq[i, 1], o, l)
+            decode_attention_fused(qs[i], kn[i], vn[i], pos, kc[i], vc[i], o, l)
 
-    print(f"suffix {suffix}: {timed(only_suffix):.2f} us alone, {timed(step):.2f} us per layer with the prefix launch", flush=True)
+    print(f"suffix {suffix}, cache view of {rows} rows: {timed(only_suffix):.2f} us alone, {timed(step):.2f} us per layer with the prefix launch", flush=True)
