@@ -270,6 +270,28 @@ def flash_attention(q: Tensor, k: Tensor, v: Tensor, causal: bool = False) -> Tu
     return res[0], res[1].permute(0, 2, 1)
 
 
+def _varlen_by_sequence(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q: int, causal: bool):
+    """flash_attention_varlen for ragged query groups / causal masks: sequence i = q rows [cu_q[i], cu_q[i+1]) against key rows
+    [cu_k[i], cu_k[i+1]), one ``flash_attention`` call each; lse [n, hq, max_seqlen_q] with -inf past a sequence's rows."""
+    cq, ck = [int(x) for x in cu_seqlens_q.tolist()], [int(x) for x in cu_seqlens_k.tolist()]
+    n = len(cq) - 1
+    if len(ck) != n + 1:
+        raise ValueError("cu_seqlens_q and cu_seqlens_k must describe the same number of sequences")
+    total_q, hq, d = q.shape
+    out = torch.zeros((total_q, hq, d), device=q.device, dtype=q.dtype)
+    lse = torch.full((n, hq, max_seqlen_q), float("-inf"), device=q.device, dtype=torch.float32)
+    for i in range(n):
+        qs, qe, ks, ke = cq[i], cq[i + 1], ck[i], ck[i + 1]
+        if qe - qs > max_seqlen_q:
+            raise ValueError(f"sequence {i} has {qe - qs} query rows, max_seqlen_q is {max_seqlen_q}")
+        if qe == qs or ke == ks:  # no rows / no keys: out = 0, lse = -inf
+            continue
+        o, l = flash_attention(q[qs:qe].unsqueeze(0), k[ks:ke].unsqueeze(0), v[ks:ke].unsqueeze(0), causal=causal)
+        out[qs:qe] = o[0]
+        lse[i, :, : qe - qs] = l[0]
+    return out, lse
+
+
 def flash_attention_varlen(
     q: Tensor,
     k: Tensor,
@@ -283,17 +305,17 @@ def flash_attention_varlen(
     """hydragen/flash.py:309-351.  q [total_q, hq, d], k/v [total_k, hkv, d]; returns
     out [total_q, hq, d] and lse [n, hq, max_seqlen_q] (the flash-attn v2.3.6 layout).
 
-    As in every call the reference makes (hydragen/attention.py:295-321), all n query groups must
-    hold exactly ``max_seqlen_q`` rows (checked without a device sync: n * max_seqlen_q ==
-    total_q); the key side is ragged and read from ``cu_seqlens_k`` on the device."""
-    if causal:
-        raise NotImplementedError("flash_attention_varlen(causal=True) is never used on the Hydragen path")
+    Every call the reference makes (hydragen/attention.py:295-321) has n equal query groups of ``max_seqlen_q`` rows and no
+    mask: that form is ONE grouped tcgen05 launch, recognised without a device sync (n * max_seqlen_q == total_q), the
+    ragged key side read from ``cu_seqlens_k`` on the device.  The general form of the primitive -- ragged query groups and / or
+    ``causal=True`` (bottom-right aligned per sequence, flash-attn >= 2.1) -- is kept for surface parity and runs one dense call
+    per sequence after reading the offsets on the host (a sync; not a hot path: nothing on the Hydragen path produces it)."""
     if q.ndim != 3 or k.ndim != 3 or v.ndim != 3:
         raise ValueError("varlen tensors must be [total, heads, d]")
     n = cu_seqlens_q.shape[0] - 1
     total_q, hq, d = q.shape
-    if n * max_seqlen_q != total_q:
-        raise NotImplementedError("ragged query groups are not supported (the Hydragen path never produces them)")
+    if causal or n * max_seqlen_q != total_q:
+        return _varlen_by_sequence(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, causal)
     out, lse = prefix_attention_grouped(q.view(n, max_seqlen_q, hq, d) if q.is_contiguous() else q.reshape(n, max_seqlen_q, hq, d),
                                         k, v, n_groups=n, cu_seqlens_k=cu_seqlens_k, max_seqlen_k=max_seqlen_k)
     return out.view(total_q, hq, d), lse.view(n, max_seqlen_q, hq).permute(0, 2, 1)

@@ -133,6 +133,38 @@ def test_flash_attention_varlen(dtype):
     assert (lse.double().cpu() - rl).abs().max().item() < 5e-3
 
 
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_flash_attention_varlen_ragged_queries_and_causal(dtype, causal):
+    """The general form of the primitive (hydragen/flash.py:309-351 -> flash_attn_varlen_func): ragged query groups, an empty
+    group, a group without keys, and the bottom-right aligned causal mask per sequence; lse [n, hq, max_seqlen_q], -inf past a
+    sequence's rows.  Never produced by the Hydragen path, kept for surface parity (one dense call per sequence)."""
+    from hydragen_b200.flash import flash_attention_varlen
+
+    g = torch.Generator().manual_seed(17)
+    qlens, klens = [1, 5, 64, 130, 0, 3], [7, 64, 64, 200, 9, 0]
+    n, hq, hkv, d = len(qlens), 4, 2, 128
+    q = torch.randn(sum(qlens), hq, d, generator=g).to(dtype)
+    k = torch.randn(sum(klens), hkv, d, generator=g).to(dtype)
+    v = torch.randn(sum(klens), hkv, d, generator=g).to(dtype)
+    cu_q = torch.tensor([0] + list(torch.tensor(qlens).cumsum(0)), dtype=torch.int32)
+    cu_k = torch.tensor([0] + list(torch.tensor(klens).cumsum(0)), dtype=torch.int32)
+    out, lse = flash_attention_varlen(q.cuda(), k.cuda(), v.cuda(), cu_q.cuda(), cu_k.cuda(), max(qlens), max(klens), causal=causal)
+    assert out.shape == q.shape and lse.shape == (n, hq, max(qlens))
+    # the oracle sequence by sequence (its own varlen walks every group, including the ones without keys, through softmax)
+    for i in range(n):
+        qs, qe, ks, ke = int(cu_q[i]), int(cu_q[i + 1]), int(cu_k[i]), int(cu_k[i + 1])
+        if qe == qs:
+            continue
+        if ke == ks:
+            assert (out[qs:qe] == 0).all() and torch.isneginf(lse[i, :, : qe - qs]).all()
+            continue
+        ro, rl = O.flash_attention(q[qs:qe][None], k[ks:ke][None], v[ks:ke][None], causal=causal)
+        _assert_close(out[qs:qe][None], ro, dtype, f"out[{i}]")
+        assert (lse[i, :, : qe - qs].double().cpu() - rl[0]).abs().max().item() < 2e-2
+        assert torch.isneginf(lse[i, :, qe - qs :]).all()
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("cfg", [(4, 1, 8, 8, 128, 40), (3, 1, 8, 1, 128, 300), (5, 2, 4, 2, 64, 17), (2, 1, 32, 32, 128, 700), (130, 1, 2, 2, 128, 9)])
 def test_flash_attention_seqlen(dtype, cfg):
