@@ -277,7 +277,14 @@ def run_ours(a):
         a.gpus = world
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
+        # one process per GPU: keep it -- and the pinned host buffers of the e2e leg, allocated below -- on the socket its GPU hangs
+        # off (r02x / r02zk: without placement the aggregate host->device rate stops at ~115 GB/s from N = 4 on).  Not at N = 1: the
+        # cpu_baseline leg of that run uses every host core.
+        from hydragen_b200.host import bind_process_to_gpu_numa
+
+        numa = bind_process_to_gpu_numa(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=dev)
 
@@ -718,6 +725,7 @@ def run_ours(a):
         cfg = bench_config(a, world)
         cfg["cuda_graph"] = used_graph
         cfg["collective"] = ("hg_allreduce_multimem NVLS kernel" if nvls is not None else "NCCL") if world > 1 else None
+        cfg["numa_bind_rank0"] = numa
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",

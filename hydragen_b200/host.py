@@ -26,6 +26,48 @@ from torch import Tensor
 from .attention import hydragen_attention_decode
 
 
+def parse_cpulist(text: str) -> List[int]:
+    """'0-3,8,10-11' (the sysfs cpulist format) -> [0, 1, 2, 3, 8, 10, 11]."""
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_process_to_gpu_numa(device_index: int, sysfs_root: str = "/sys/bus/pci/devices") -> Optional[dict]:
+    """Restrict this process to the CPUs that are local to GPU ``device_index`` (its PCIe root's NUMA node, read from sysfs), so
+    that the pinned host buffers allocated afterwards -- first touch -- sit on the socket the GPU hangs off.  One process per GPU
+    (torchrun); call it before allocating pinned memory.  Returns what was done, or None when there is nothing to do or anything
+    about the platform is unexpected (no sysfs entry, no NUMA information, CPUs outside this process's cpuset): it never raises.
+    ``HYDRAGEN_B200_BIND_NUMA=0`` disables it."""
+    import os
+
+    if os.environ.get("HYDRAGEN_B200_BIND_NUMA", "1") == "0":
+        return None
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(os.path.join(sysfs_root, bdf, "local_cpulist")) as f:
+            local = set(parse_cpulist(f.read()))
+        allowed = os.sched_getaffinity(0)
+        target = local & allowed
+        if not target or target == allowed:
+            return None
+        os.sched_setaffinity(0, target)
+        node = None
+        try:
+            with open(os.path.join(sysfs_root, bdf, "numa_node")) as f:
+                node = int(f.read().strip())
+        except Exception:
+            pass
+        return {"pci": bdf, "numa_node": node, "cpus": len(target), "of": len(allowed)}
+    except Exception:
+        return None
+
+
 @dataclass
 class HostDecodeLayer:
     """One layer's operands.  ``*_host`` are pinned host tensors, ``*_dev`` the device staging buffers of the

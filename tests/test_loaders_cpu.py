@@ -85,3 +85,42 @@ def test_generate_capacity_checks():
         model.generate(ids, num_return_sequences=5, max_new_tokens=4)
     with pytest.raises(ValueError, match="unique cache"):
         model.process_unique(torch.randint(3, 90, (2, 17)))
+
+
+def test_numa_binding_helper_is_inert_without_a_gpu_and_parses_cpulists(tmp_path, monkeypatch):
+    """hydragen_b200.host.bind_process_to_gpu_numa never raises: no CUDA device, no sysfs entry, switched off -> None; the sysfs
+    cpulist format is parsed as the kernel documents it."""
+    from hydragen_b200.host import bind_process_to_gpu_numa, parse_cpulist
+
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist("") == [] and parse_cpulist("5") == [5]
+    assert bind_process_to_gpu_numa(0, sysfs_root=str(tmp_path)) is None  # no GPU here / no such PCI device
+    monkeypatch.setenv("HYDRAGEN_B200_BIND_NUMA", "0")
+    assert bind_process_to_gpu_numa(0) is None
+
+
+def test_numa_binding_helper_binds_to_the_gpu_local_cpus(tmp_path, monkeypatch):
+    """With a (faked) sysfs entry naming a subset of this process's CPUs as local to the GPU, the process is restricted to them."""
+    import os
+    import types
+
+    import torch
+
+    from hydragen_b200.host import bind_process_to_gpu_numa
+
+    allowed = sorted(os.sched_getaffinity(0))
+    if len(allowed) < 2:
+        pytest.skip("needs at least two CPUs")
+    local = allowed[: len(allowed) // 2]
+    dev = tmp_path / "0000:1b:00.0"
+    dev.mkdir()
+    (dev / "local_cpulist").write_text(",".join(str(c) for c in local) + ",100000\n")  # a CPU outside the cpuset is ignored
+    (dev / "numa_node").write_text("1\n")
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1B, pci_device_id=0))
+    try:
+        got = bind_process_to_gpu_numa(0, sysfs_root=str(tmp_path))
+        assert got == {"pci": "0000:1b:00.0", "numa_node": 1, "cpus": len(local), "of": len(allowed)}
+        assert sorted(os.sched_getaffinity(0)) == local
+        assert bind_process_to_gpu_numa(0, sysfs_root=str(tmp_path)) is None  # already there: nothing to do
+    finally:
+        os.sched_setaffinity(0, allowed)
